@@ -1,0 +1,238 @@
+"""AnnealedImportanceSampler on the B200 kernels -- same constructor, attributes and return values
+as fab/sampling_methods/ais.py:20-213, so it can replace `FABModel.annealed_importance_sampler`
+(fab/core.py:65-73) or be bound over `fab.core.AnnealedImportanceSampler`.
+
+One `sample_and_log_weights` call enqueues, without any host synchronisation in between:
+  init kernel (flow sample + Point + log_w, ais.py:56-64)  ->  NaN/inf filter (ais.py:65,190-213,
+  stable compaction on the device, live count kept in device memory)  ->  base ESS partial
+  ->  M fused transitions (each also applies the log-weight update ais.py:93-100)
+  ->  filter  ->  ESS / log Z reduction (ais.py:80-86, numerical.py:18-23)
+and then reads back ONE small record (live counts, ESS, logsumexp) -- the only sync of the call.
+With a process group, particles are sharded over ranks; the exchanges are the scalar triples of
+SURVEY §8e (an all-gather of 4 floats per ESS, an all-reduce of 4 floats per HMC outer step when
+the step-size tuner is on).
+"""
+from typing import Any, Dict, NamedTuple, Optional, Tuple
+
+import numpy as np
+import torch
+
+from fab_torch_b200 import _lib
+from fab_torch_b200.point import Point
+from fab_torch_b200.transition_operators import TransitionOperator, make_gamma
+
+
+class LoggingInfo(NamedTuple):
+    ess_base: float
+    ess_ais: float
+    log_Z: float
+
+
+def setup_distribution_spacing(distribution_spacing_type: str,
+                               n_intermediate_distributions: int) -> torch.Tensor:
+    """beta grid of M+2 points, float64 (ais.py:108-129)."""
+    assert n_intermediate_distributions > 0
+    M = n_intermediate_distributions
+    if distribution_spacing_type == "geometric":
+        n_lin = int(M / 4)
+        n_geo = M - n_lin - 1
+        B_space = np.concatenate([np.linspace(0, 0.01, n_lin + 2)[:-1],
+                                  np.geomspace(0.01, 1, n_geo + 2)])
+    elif distribution_spacing_type == "linear":
+        B_space = np.linspace(0.0, 1.0, M + 2)
+    else:
+        raise Exception(f"distribution spacing incorrectly specified:"
+                        f" '{distribution_spacing_type}',"
+                        f"options are 'geometric' or 'linear'")
+    assert B_space.shape == (M + 2,)
+    return torch.tensor(B_space)
+
+
+class AnnealedImportanceSampler:
+    def __init__(self, base_distribution, target_log_prob, transition_operator: TransitionOperator,
+                 p_target: bool, alpha: Optional[float] = None,
+                 n_intermediate_distributions: int = 1,
+                 distribution_spacing_type: str = "linear",
+                 process_group=None):
+        if not p_target:
+            assert alpha is not None, "Must specify alpha if AIS target is not p."
+        self.base_distribution = base_distribution
+        self.target_log_prob = target_log_prob
+        self.transition_operator = transition_operator
+        self.p_target = p_target
+        self.alpha = alpha
+        self.n_intermediate_distributions = n_intermediate_distributions
+        self.distribution_spacing_type = distribution_spacing_type
+        self.B_space = setup_distribution_spacing(distribution_spacing_type,
+                                                  n_intermediate_distributions)
+        self._logging_info: LoggingInfo
+        self.process_group = process_group
+        if not (hasattr(base_distribution, "desc") and hasattr(base_distribution, "blob")):
+            raise TypeError("base_distribution must be a B200RealNVP")
+        target = getattr(target_log_prob, "__self__", None)
+        if target is None or not hasattr(target, "target_desc"):
+            raise TypeError("target_log_prob must be the log_prob of a fab_torch_b200 target")
+        self._target = target
+        self._host = None      # pinned read-back record
+        self._filter_ws = None
+
+    # ------------------------------------------------------------------------------------------
+    def get_logging_info(self) -> Dict[str, Any]:
+        logging_info = self._logging_info._asdict()
+        logging_info.update(self.transition_operator.get_logging_info())
+        return logging_info
+
+    def _world(self):
+        if self.process_group is None:
+            return 1, 0
+        import torch.distributed as dist
+        return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+
+    def _filter(self, pt: Point, log_w, n_in, n_out):
+        L = _lib.lib()
+        n, d = pt.x.shape
+        nbytes = int(L.fab_filter_workspace_bytes(n, d))
+        if self._filter_ws is None or self._filter_ws.numel() < nbytes or \
+                self._filter_ws.device != pt.x.device:
+            self._filter_ws = torch.empty(nbytes, dtype=torch.uint8, device=pt.x.device)
+        rc = L.fab_nan_filter_f32(_lib.point_ptrs(pt), _lib.ptr(log_w), d, n,
+                                  _lib.ptr(n_in) if n_in is not None else None, _lib.ptr(n_out),
+                                  _lib.ptr(self._filter_ws), _lib.stream_ptr(pt.x.device))
+        _lib.check(rc, "fab_nan_filter_f32")
+
+    def _ess(self, values, sub, n_active, out3):
+        """ESS / logsumexp of (values - sub) over the live particles of ALL ranks -> out3."""
+        L = _lib.lib()
+        dev = values.device
+        world, rank = self._world()
+        part = torch.empty(4, dtype=torch.float32, device=dev)
+        rc = L.fab_ess_partial_f32(_lib.ptr(values), _lib.ptr(sub) if sub is not None else None,
+                                   values.shape[0], _lib.ptr(n_active), _lib.ptr(part),
+                                   _lib.stream_ptr(dev))
+        _lib.check(rc, "fab_ess_partial_f32")
+        if world > 1:
+            import torch.distributed as dist
+            parts = torch.empty(4 * world, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(parts, part, group=self.process_group)
+        else:
+            parts = part
+        rc = L.fab_ess_finalize_f32(_lib.ptr(parts), world, _lib.ptr(out3), _lib.stream_ptr(dev))
+        _lib.check(rc, "fab_ess_finalize_f32")
+
+    def _w_update(self, j: int):
+        """(gamma_j, gamma_{j+1}) with the SAMPLER's alpha/p_target, or None when beta does not
+        move (ais.py:93-105)."""
+        if bool(self.B_space[j + 1] == self.B_space[j]):
+            return None
+        return (make_gamma(self.B_space[j], self.alpha, self.p_target),
+                make_gamma(self.B_space[j + 1], self.alpha, self.p_target))
+
+    def _run_chain(self, batch_size: int, logging: bool):
+        """Enqueue the whole chain; returns device tensors + the device record (no sync)."""
+        flow, op, target = self.base_distribution, self.transition_operator, self._target
+        dev = flow._device()
+        L = _lib.lib()
+        d = flow.dim
+        n = batch_size
+        with_grad = bool(op.uses_grad_info)
+        noise = op.noise
+        eps = getattr(flow, "_eps_override", None)
+        if eps is not None:
+            flow._eps_override = None
+        else:
+            eps = noise.base_eps(n, d, dev)
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        pt = Point(f(n, d), f(n), f(n), f(n, d) if with_grad else None,
+                   f(n, d) if with_grad else None)
+        log_w, log_q0 = f(n), f(n)
+        valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        counts = torch.zeros(2, dtype=torch.int32, device=dev)
+        rec = torch.zeros(8, dtype=torch.float32, device=dev)
+        g1 = make_gamma(self.B_space[1], self.alpha, self.p_target)
+        rc = L.fab_ais_init_f32(flow.desc(), _lib.ptr(flow.blob()), target.target_desc(dev),
+                                _lib.ptr(eps.contiguous()), g1, 1 if with_grad else 0,
+                                _lib.point_ptrs(pt), _lib.ptr(log_w), _lib.ptr(log_q0),
+                                _lib.ptr(valid), n, _lib.stream_ptr(dev))
+        _lib.check(rc, "fab_ais_init_f32")
+        self._filter(pt, log_w, None, counts[0:1])                 # "chain init"
+        if logging:
+            self._ess(pt.log_p, pt.log_q, counts[0:1], rec[0:3])   # ESS over base weights
+        M = self.n_intermediate_distributions
+        for j in range(1, M + 1):
+            op.run(pt, j, self.B_space[j], log_w, self._w_update(j), n_active=counts[0:1])
+        self._filter(pt, log_w, counts[0:1], counts[1:2])          # "chain end"
+        if logging:
+            self._ess(log_w, None, counts[1:2], rec[3:6])
+        return pt, log_w, counts, rec
+
+    def sample_and_log_weights(self, batch_size: int, logging: bool = True
+                               ) -> Tuple[Point, torch.Tensor]:
+        world, rank = self._world()
+        op = self.transition_operator
+        op.process_group = self.process_group
+        local = batch_size
+        if world > 1:
+            assert batch_size % world == 0, "batch_size must be divisible by the world size"
+            local = batch_size // world
+        pt, log_w, counts, rec = self._run_chain(local, logging)
+        dev = log_w.device
+        if self._host is None:
+            self._host = torch.empty(10, dtype=torch.float32).pin_memory()
+        both = torch.cat([counts.to(torch.float32), rec])
+        self._host.copy_(both, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()               # the one sync of the call
+        h = self._host.numpy()
+        n_init, n_end = int(h[0]), int(h[1])
+        if n_init == 0:
+            raise Exception("No valid points generated in sampling the chain init")
+        if n_end == 0:
+            raise Exception("No valid points generated in sampling the chain end")
+        if n_init != local:
+            print(f"{local - n_init} nan/inf samples/log-probs/log-weights encountered at chain init.")
+        if n_end != n_init:
+            print(f"{n_init - n_end} nan/inf samples/log-probs/log-weights encountered at chain end.")
+        if logging:
+            log_Z = np.float32(h[2 + 4]) - np.log(np.float32(batch_size))     # ais.py:83-84 (quirk 6)
+            self._logging_info = LoggingInfo(ess_base=float(h[2 + 0]), ess_ais=float(h[2 + 3]),
+                                             log_Z=float(log_Z))
+        if n_end != local:
+            pt = pt[slice(0, n_end)]
+            log_w = log_w[:n_end]
+        return pt, log_w.detach()
+
+    # kept for API parity with the reference sampler (ais.py:90-105); runs one fused transition
+    def perform_transition(self, x_new: Point, log_w: torch.Tensor, j: int):
+        x_new = self.transition_operator.run(x_new, j, self.B_space[j], log_w, self._w_update(j))
+        return x_new, log_w
+
+    def generate_eval_data(self, outer_batch_size: int, inner_batch_size: int):
+        """ais.py:132-188: batched chains for evaluation; results concatenated on the CPU."""
+        base_samples, base_log_w_s, ais_samples, ais_log_w = [], [], [], []
+        assert outer_batch_size % inner_batch_size == 0
+        for _ in range(outer_batch_size // inner_batch_size):
+            flow, op = self.base_distribution, self.transition_operator
+            with torch.no_grad():
+                x, log_q0 = flow.sample_and_log_prob((inner_batch_size,))
+            point = op.create_new_point(x)
+            if not op.uses_grad_info:
+                point.log_q = log_q0.detach()
+            base_log_w = point.log_p - log_q0
+            ok = torch.isfinite(point.log_p) & torch.isfinite(point.log_q)
+            if bool(ok.any()) and not bool(ok.all()):
+                point, base_log_w = point[ok], base_log_w[ok]
+                point = Point(*(None if t is None else t.contiguous() for t in
+                                (point.x, point.log_q, point.log_p, point.grad_log_q,
+                                 point.grad_log_p)))
+            base_samples.append(point.x.detach().cpu())
+            base_log_w_s.append(base_log_w.detach().cpu())
+            g1 = make_gamma(self.B_space[1], self.alpha, self.p_target)
+            log_w = (g1.cq * point.log_q + g1.cp * point.log_p - point.log_q).contiguous()
+            for j in range(1, self.n_intermediate_distributions + 1):
+                point, log_w = self.perform_transition(point, log_w, j)
+            ok = torch.isfinite(point.log_p) & torch.isfinite(point.log_q)
+            if bool(ok.any()) and not bool(ok.all()):
+                point, log_w = point[ok], log_w[ok]
+            ais_samples.append(point.x.detach().cpu())
+            ais_log_w.append(log_w.detach().cpu())
+        return (torch.cat(base_samples, dim=0), torch.cat(base_log_w_s, dim=0),
+                torch.cat(ais_samples, dim=0), torch.cat(ais_log_w, dim=0))

@@ -1,0 +1,394 @@
+// libfab_b200.so -- C ABI (include/fab_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "tile_kernels.cuh"
+#include "misc_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(FAB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK_LAUNCH(what)                                             \
+    do {                                                            \
+        cudaError_t _e = cudaGetLastError();                        \
+        if (_e != cudaSuccess) return cuda_fail(_e, what);          \
+    } while (0)
+
+constexpr int kMaxSmemBytes = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+bool flow_ok(const fab_flow_desc* f) {
+    return f && f->dim >= 2 && f->d1 + f->d2 == f->dim && f->d2 >= 1 && f->n_layers >= 0 &&
+           (f->n_layers == 0 || f->width >= 1);
+}
+
+// Pick the particles-per-CTA variant: minimise (waves x T) = time of the FFMA-bound tile loop,
+// among the variants whose shared-memory layout fits; ties go to the larger tile (less L2 traffic).
+template <typename StateFn>
+int pick_tile(const fab_flow_desc& f, long long n, bool with_grad, StateFn state_floats,
+              TileLayout* out) {
+    const int cands[4] = {16, 14, 8, 4};
+    long long best_cost = -1; int best = 0;
+    for (int c = 0; c < 4; ++c) {
+        const int T = cands[c];
+        TileLayout L = make_tile_layout(f, T, with_grad, state_floats(T, fab_round4(f.dim)));
+        if ((long long)L.total_floats * 4 > kMaxSmemBytes) continue;
+        const long long ctas = (n + T - 1) / T;
+        const long long waves = (ctas + sm_count() - 1) / sm_count();
+        const long long cost = waves * T;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = T; *out = L; }
+    }
+    return best;
+}
+
+template <typename K>
+int set_smem(K kernel, const TileLayout& L) {
+    const int bytes = L.total_floats * 4;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    return FAB_OK;
+}
+
+inline int sample_state(int T, int) { return fab_round4(T); }
+
+#define DISPATCH_T(T, ...)                       \
+    switch (T) {                                 \
+        case 16: { constexpr int TT = 16; __VA_ARGS__; } break; \
+        case 14: { constexpr int TT = 14; __VA_ARGS__; } break; \
+        case 8:  { constexpr int TT = 8;  __VA_ARGS__; } break; \
+        case 4:  { constexpr int TT = 4;  __VA_ARGS__; } break; \
+        default: return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow"); \
+    }
+
+}  // namespace
+
+extern "C" {
+
+int fab_version(void) { return 100; }
+const char* fab_last_error(void) { return g_err.c_str(); }
+
+int64_t fab_flow_desc_init(fab_flow_desc* d, int32_t dim, int32_t width, int32_t n_layers) {
+    if (!d || dim < 2 || n_layers < 0 || (n_layers > 0 && width < 1))
+        return fail(FAB_E_INVALID, "fab_flow_desc_init: need dim>=2, n_layers>=0, width>=1");
+    std::memset(d, 0, sizeof(*d));
+    d->dim = dim;
+    d->d1 = (int32_t)((double)dim / 2 + 0.5);      // make_normflow_model.py:21
+    d->d2 = dim - d->d1;
+    d->width = n_layers > 0 ? width : 0;
+    d->width_pad = n_layers > 0 ? fab_round4(width) : 0;
+    d->n_layers = n_layers;
+    const int64_t DP = fab_round4(dim), D1P = fab_round4(d->d1), P2 = fab_round4(2 * d->d2),
+                  WP = d->width_pad;
+    int64_t o = 0;
+    d->off_base_loc = o; o += DP;
+    d->off_base_log_scale = o; o += DP;
+    d->off_layers = o;
+    int64_t l = 0;
+    auto packed = [](int64_t K, int64_t NP) { return ((K + 3) / 4) * NP * 4; };
+    d->o_mix = l;     l += packed(dim, DP);
+    d->o_mix_t = l;   l += packed(dim, DP);
+    d->o_mix_inv = l; l += packed(dim, DP);
+    d->o_w1 = l;      l += packed(d->d1, WP);
+    d->o_w2 = l;      l += packed(WP, WP);
+    d->o_w3 = l;      l += packed(WP, P2);
+    d->o_w3t = l;     l += packed(2 * d->d2, WP);
+    d->o_w2t = l;     l += packed(WP, WP);
+    d->o_w1t = l;     l += packed(WP, D1P);
+    d->o_b1 = l;      l += WP;
+    d->o_b2 = l;      l += WP;
+    d->o_b3 = l;      l += P2;
+    d->o_logs = l;    l += 4;
+    d->layer_stride = l;
+    d->total_floats = o + (int64_t)n_layers * l;
+    return d->total_floats;
+}
+
+int fab_tile_particles(const fab_flow_desc* flow, int64_t n) {
+    if (!flow_ok(flow) || n <= 0) return fail(FAB_E_INVALID, "fab_tile_particles: bad arguments");
+    TileLayout L;
+    return pick_tile(*flow, n, true, hmc_state_floats, &L);
+}
+
+int fab_flow_sample_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_eps,
+                        float* d_x, float* d_log_q, int64_t n, void* stream) {
+    if (!flow_ok(flow) || !d_blob || !d_eps || !d_x || !d_log_q || n < 0)
+        return fail(FAB_E_INVALID, "fab_flow_sample_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    TileLayout L;
+    const int T = pick_tile(*flow, n, false, sample_state, &L);
+    const unsigned grid = (unsigned)((n + T - 1) / T);
+    DISPATCH_T(T, {
+        if (int e = set_smem(k_flow_sample<TT>, L)) return e;
+        k_flow_sample<TT><<<grid, FAB_NT, L.total_floats * 4, (cudaStream_t)stream>>>(
+            L, *flow, d_blob, d_eps, d_x, d_log_q, (long long)n);
+    });
+    CK_LAUNCH("k_flow_sample");
+    return FAB_OK;
+}
+
+int fab_flow_logprob_grad_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_x,
+                              float* d_log_q, float* d_grad, int64_t n, void* stream) {
+    if (!flow_ok(flow) || !d_blob || !d_x || !d_log_q || n < 0)
+        return fail(FAB_E_INVALID, "fab_flow_logprob_grad_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    TileLayout L;
+    const bool grad = d_grad != nullptr;
+    const int T = pick_tile(*flow, n, grad, sample_state, &L);
+    const unsigned grid = (unsigned)((n + T - 1) / T);
+    const size_t sm = (size_t)L.total_floats * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(T, {
+        if (grad) {
+            if (int e = set_smem(k_flow_logprob<TT, true>, L)) return e;
+            k_flow_logprob<TT, true><<<grid, FAB_NT, sm, s>>>(L, *flow, d_blob, d_x, d_log_q, d_grad,
+                                                              (long long)n);
+        } else {
+            if (int e = set_smem(k_flow_logprob<TT, false>, L)) return e;
+            k_flow_logprob<TT, false><<<grid, FAB_NT, sm, s>>>(L, *flow, d_blob, d_x, d_log_q,
+                                                               nullptr, (long long)n);
+        }
+    });
+    CK_LAUNCH("k_flow_logprob");
+    return FAB_OK;
+}
+
+static bool target_ok(const fab_target_desc* t) {
+    if (!t || t->dim < 1) return false;
+    if (t->kind == FAB_TARGET_MANYWELL) return true;
+    if (t->kind == FAB_TARGET_GMM)
+        return t->n_mixes >= 1 && t->d_locs && t->d_scales && t->d_log_weights;
+    return false;
+}
+
+int fab_target_logprob_grad_f32(const fab_target_desc* target, const float* d_x, float* d_log_p,
+                                float* d_grad, int64_t n, void* stream) {
+    if (!target_ok(target) || !d_x || !d_log_p || n < 0)
+        return fail(FAB_E_INVALID, "fab_target_logprob_grad_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    const int nt = 256;
+    const long long threads = n * 32;
+    k_target<<<(unsigned)((threads + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+        *target, d_x, d_log_p, d_grad, (long long)n);
+    CK_LAUNCH("k_target");
+    return FAB_OK;
+}
+
+int fab_ais_init_f32(const fab_flow_desc* flow, const float* d_blob, const fab_target_desc* target,
+                     const float* d_eps, fab_gamma g1, int32_t with_grad, fab_point out,
+                     float* d_log_w, float* d_log_q0, uint8_t* d_valid, int64_t n, void* stream) {
+    if (!flow_ok(flow) || !target_ok(target) || target->dim != flow->dim || !d_blob || !d_eps ||
+        !out.d_x || !out.d_log_q || !out.d_log_p || !d_log_w || !d_valid || n < 0 ||
+        (with_grad && (!out.d_grad_log_q || !out.d_grad_log_p)))
+        return fail(FAB_E_INVALID, "fab_ais_init_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    TileLayout L;
+    const int T = pick_tile(*flow, n, with_grad != 0, init_state_floats, &L);
+    const unsigned grid = (unsigned)((n + T - 1) / T);
+    const size_t sm = (size_t)L.total_floats * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(T, {
+        if (with_grad) {
+            if (int e = set_smem(k_ais_init<TT, true>, L)) return e;
+            k_ais_init<TT, true><<<grid, FAB_NT, sm, s>>>(L, *flow, d_blob, *target, d_eps, g1, out,
+                                                          d_log_w, d_log_q0, d_valid, (long long)n);
+        } else {
+            if (int e = set_smem(k_ais_init<TT, false>, L)) return e;
+            k_ais_init<TT, false><<<grid, FAB_NT, sm, s>>>(L, *flow, d_blob, *target, d_eps, g1, out,
+                                                           d_log_w, d_log_q0, d_valid, (long long)n);
+        }
+    });
+    CK_LAUNCH("k_ais_init");
+    return FAB_OK;
+}
+
+int64_t fab_hmc_workspace_bytes(const fab_flow_desc* flow, int64_t n) {
+    (void)flow;
+    if (n < 0) return FAB_E_INVALID;
+    return ((n + 3) / 4) * 2 * (int64_t)sizeof(float) + 64;   // smallest tile (4) => most CTAs
+}
+
+int fab_hmc_step_f32(const fab_flow_desc* flow, const float* d_blob, const fab_target_desc* target,
+                     fab_hmc_state st, fab_hmc_args a, fab_point cur, fab_point prop_in,
+                     fab_point prop_out, float* d_log_w, const float* d_mom_noise,
+                     const float* d_exp_noise, const int32_t* d_n_active, float* d_stats,
+                     void* d_workspace, int64_t n, void* stream) {
+    if (!flow_ok(flow) || !target_ok(target) || target->dim != flow->dim || !d_blob ||
+        !st.d_epsilons || !st.d_common_epsilon || !st.d_mass || !st.d_log || st.n_outer < 1 ||
+        a.i < 1 || a.i > st.n_dist || a.outer < 0 || a.outer >= st.n_outer || a.L < 1 ||
+        !cur.d_x || !cur.d_log_q || !cur.d_log_p || !cur.d_grad_log_q || !cur.d_grad_log_p ||
+        !d_mom_noise || !d_exp_noise || !d_stats || !d_workspace || n < 0 ||
+        (a.update_log_w && !d_log_w))
+        return fail(FAB_E_INVALID, "fab_hmc_step_f32: bad arguments");
+    if (prop_in.d_x && (!prop_in.d_log_q || !prop_in.d_log_p || !prop_in.d_grad_log_q ||
+                        !prop_in.d_grad_log_p))
+        return fail(FAB_E_INVALID, "fab_hmc_step_f32: incomplete prop_in");
+    if (prop_out.d_x && (!prop_out.d_log_q || !prop_out.d_log_p || !prop_out.d_grad_log_q ||
+                         !prop_out.d_grad_log_p))
+        return fail(FAB_E_INVALID, "fab_hmc_step_f32: incomplete prop_out");
+    if (n == 0) return FAB_OK;
+    TileLayout L;
+    const int T = pick_tile(*flow, n, true, hmc_state_floats, &L);
+    const unsigned grid = (unsigned)((n + T - 1) / T);
+    const size_t sm = (size_t)L.total_floats * 4;
+    DISPATCH_T(T, {
+        if (int e = set_smem(k_hmc_step<TT>, L)) return e;
+        k_hmc_step<TT><<<grid, FAB_NT, sm, (cudaStream_t)stream>>>(
+            L, *flow, d_blob, *target, st, a, cur, prop_in, prop_out, d_log_w, d_mom_noise,
+            d_exp_noise, d_n_active, d_stats, (float*)d_workspace, (long long)n);
+    });
+    CK_LAUNCH("k_hmc_step");
+    return FAB_OK;
+}
+
+int fab_hmc_finish_f32(fab_hmc_state st, fab_hmc_args a, const float* d_stats, void* stream) {
+    if (!st.d_epsilons || !st.d_common_epsilon || !st.d_log || !d_stats)
+        return fail(FAB_E_INVALID, "fab_hmc_finish_f32: bad arguments");
+    k_hmc_finish<<<1, 32, 0, (cudaStream_t)stream>>>(st, a, d_stats);
+    CK_LAUNCH("k_hmc_finish");
+    return FAB_OK;
+}
+
+int64_t fab_metropolis_workspace_bytes(const fab_flow_desc* flow, int64_t n, int32_t n_updates) {
+    (void)flow; (void)n_updates;
+    if (n < 0) return FAB_E_INVALID;
+    return ((n + 3) / 4) * FAB_MAX_UPDATES * (int64_t)sizeof(float) + 64;
+}
+
+int fab_metropolis_transition_f32(const fab_flow_desc* flow, const float* d_blob,
+                                  const fab_target_desc* target, fab_metropolis_args a,
+                                  float* d_noise_scalings, fab_point cur, float* d_log_w,
+                                  const float* d_prop_noise, const float* d_unif,
+                                  const int32_t* d_n_active, float* d_stats, void* d_workspace,
+                                  int64_t n, void* stream) {
+    if (!flow_ok(flow) || !target_ok(target) || target->dim != flow->dim || !d_blob ||
+        !d_noise_scalings || a.i < 1 || a.n_updates < 1 || a.n_updates > FAB_MAX_UPDATES ||
+        !cur.d_x || !cur.d_log_q || !cur.d_log_p || !d_prop_noise || !d_unif || !d_stats ||
+        !d_workspace || n < 0 || (a.update_log_w && !d_log_w))
+        return fail(FAB_E_INVALID, "fab_metropolis_transition_f32: bad arguments (n_updates <= 16)");
+    if (n == 0) return FAB_OK;
+    TileLayout L;
+    const int T = pick_tile(*flow, n, false, metro_state_floats, &L);
+    const unsigned grid = (unsigned)((n + T - 1) / T);
+    const size_t sm = (size_t)L.total_floats * 4;
+    DISPATCH_T(T, {
+        if (int e = set_smem(k_metropolis<TT>, L)) return e;
+        k_metropolis<TT><<<grid, FAB_NT, sm, (cudaStream_t)stream>>>(
+            L, *flow, d_blob, *target, a, d_noise_scalings, cur, d_log_w, d_prop_noise, d_unif,
+            d_n_active, d_stats, (float*)d_workspace, (long long)n);
+    });
+    CK_LAUNCH("k_metropolis");
+    return FAB_OK;
+}
+
+int fab_metropolis_finish_f32(fab_metropolis_args a, float* d_noise_scalings, const float* d_stats,
+                              void* stream) {
+    if (!d_noise_scalings || !d_stats || a.n_updates < 1 || a.n_updates > FAB_MAX_UPDATES)
+        return fail(FAB_E_INVALID, "fab_metropolis_finish_f32: bad arguments");
+    k_metropolis_finish<<<1, 32, 0, (cudaStream_t)stream>>>(a, d_noise_scalings, d_stats);
+    CK_LAUNCH("k_metropolis_finish");
+    return FAB_OK;
+}
+
+int fab_logw_update_f32(fab_gamma g, fab_gamma g_next, const float* d_log_q, const float* d_log_p,
+                        float* d_log_w, int64_t n, void* stream) {
+    if (!d_log_q || !d_log_p || !d_log_w || n < 0)
+        return fail(FAB_E_INVALID, "fab_logw_update_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    k_logw_update<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        g, g_next, d_log_q, d_log_p, d_log_w, (long long)n);
+    CK_LAUNCH("k_logw_update");
+    return FAB_OK;
+}
+
+int64_t fab_filter_workspace_bytes(int64_t n, int32_t dim) {
+    if (n < 0 || dim < 1) return FAB_E_INVALID;
+    return n * 4 + 64 + n * (3 * (int64_t)dim + 3) * 4;
+}
+
+int fab_nan_filter_f32(fab_point pt, float* d_log_w, int32_t dim, int64_t n, const int32_t* d_n_in,
+                       int32_t* d_n_out, void* d_workspace, void* stream) {
+    if (!pt.d_x || !pt.d_log_q || !pt.d_log_p || !d_log_w || dim < 1 || n < 0 || !d_n_out ||
+        !d_workspace || n > 0x7fffffffLL)
+        return fail(FAB_E_INVALID, "fab_nan_filter_f32: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* pos = (int*)d_workspace;
+    int* meta = pos + n;
+    float* stage = (float*)(meta + 16);
+    k_filter_scan<<<1, FAB_SCAN_NT, 0, s>>>(pt.d_log_q, pt.d_log_p, (long long)n, d_n_in, d_n_out,
+                                            pos, meta);
+    CK_LAUNCH("k_filter_scan");
+    if (n == 0) return FAB_OK;
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    k_filter_stage<<<grid, 256, 0, s>>>(pt, d_log_w, dim, pos, meta, stage, (long long)n);
+    CK_LAUNCH("k_filter_stage");
+    k_filter_unstage<<<grid, 256, 0, s>>>(pt, d_log_w, dim, meta, stage, (long long)n);
+    CK_LAUNCH("k_filter_unstage");
+    return FAB_OK;
+}
+
+int fab_ess_partial_f32(const float* d_log_w, const float* d_sub, int64_t n,
+                        const int32_t* d_n_active, float* d_partial4, void* stream) {
+    if (!d_log_w || !d_partial4 || n < 0)
+        return fail(FAB_E_INVALID, "fab_ess_partial_f32: bad arguments");
+    k_ess_partial<<<1, FAB_SCAN_NT, 0, (cudaStream_t)stream>>>(d_log_w, d_sub, (long long)n,
+                                                               d_n_active, d_partial4);
+    CK_LAUNCH("k_ess_partial");
+    return FAB_OK;
+}
+
+int fab_ess_finalize_f32(const float* d_partials4, int32_t n_parts, float* d_out3, void* stream) {
+    if (!d_partials4 || n_parts < 1 || !d_out3)
+        return fail(FAB_E_INVALID, "fab_ess_finalize_f32: bad arguments");
+    k_ess_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(d_partials4, n_parts, d_out3);
+    CK_LAUNCH("k_ess_finalize");
+    return FAB_OK;
+}
+
+int64_t fab_resample_workspace_bytes(int64_t n) {
+    if (n < 0) return FAB_E_INVALID;
+    return (n + 2) * 8;
+}
+
+int fab_resample_systematic_u64(const float* d_log_w, int64_t n, uint32_t u0, int64_t* d_anc,
+                                void* d_workspace, void* stream) {
+    if (!d_log_w || !d_anc || !d_workspace || n < 1 || n > (1LL << 24))
+        return fail(FAB_E_INVALID, "fab_resample_systematic_u64: need 1 <= n <= 2^24");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* cdf = (unsigned long long*)d_workspace;
+    k_resample_cdf<<<1, FAB_SCAN_NT, 0, s>>>(d_log_w, (long long)n, cdf);
+    CK_LAUNCH("k_resample_cdf");
+    k_resample_search<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cdf, (long long)n, u0,
+                                                                   (long long*)d_anc);
+    CK_LAUNCH("k_resample_search");
+    return FAB_OK;
+}
+
+int fab_gather_rows_f32(const float* d_src, float* d_dst, const int64_t* d_anc, int64_t n,
+                        int32_t row_floats, void* stream) {
+    if (!d_src || !d_dst || !d_anc || n < 0 || row_floats < 1)
+        return fail(FAB_E_INVALID, "fab_gather_rows_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    const long long tot = n * row_floats;
+    k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_src, d_dst, (const long long*)d_anc, (long long)n, row_floats);
+    CK_LAUNCH("k_gather_rows");
+    return FAB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,491 @@
+// Global kernels built on the tile device functions: flow sample / log_prob(+grad), chain
+// initialisation, the fused HMC outer step and the fused Metropolis transition.
+#pragma once
+#include "flow_tile.cuh"
+#include "target_tile.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_rows(float* dst, int ldd, const float* __restrict__ src, int d,
+                                          long long row0, int np, int T) {
+    // dst[T][ldd] <- src[row0 .. row0+np)[d], zero elsewhere (incl. pad columns)
+    for (int i = threadIdx.x; i < T * ldd; i += FAB_NT) {
+        const int p = i / ldd, j = i - p * ldd;
+        dst[i] = (p < np && j < d) ? __ldg(src + (row0 + p) * d + j) : 0.f;
+    }
+}
+__device__ __forceinline__ void store_rows(float* __restrict__ dst, int d, const float* src, int lds,
+                                           long long row0, int np) {
+    for (int i = threadIdx.x; i < np * d; i += FAB_NT) {
+        const int p = i / d, j = i - p * d;
+        dst[(row0 + p) * d + j] = src[p * lds + j];
+    }
+}
+__device__ __forceinline__ void copy_tile(float* dst, const float* src, int n) {
+    for (int i = threadIdx.x; i < n; i += FAB_NT) dst[i] = src[i];
+}
+
+// Evaluate log q (+grad), log p (+grad) at the rows x[T][DP] (shared).  Outputs in shared:
+// lq[T], lp[T], gq[T][DP], gp[T][DP] (the last two only when GRAD).
+template <int T, bool GRAD>
+__device__ void eval_point(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
+                           const float* __restrict__ blob, const fab_target_desc& tgt,
+                           const float* x, float* lq, float* lp, float* gq, float* gp) {
+    copy_tile(b.zs, x, T * L.DP);
+    __syncthreads();
+    flow_inverse<T, GRAD>(L, b, f, blob, lq);
+    if (GRAD) {
+        flow_backward<T>(L, b, f, blob);
+        copy_tile(gq, b.vs, T * L.DP);
+    }
+    target_tile<T>(tgt, x, L.DP, L.d, lp, GRAD ? gp : nullptr);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2  flow sample      K3/K4  flow log_prob (+ input gradient)
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(FAB_NT, 1)
+k_flow_sample(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
+              const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ log_q,
+              long long n) {
+    extern __shared__ __align__(16) float smem[];
+    const TileBufs b = tile_bufs(L, smem);
+    float* lq = smem + L.o_state;
+    const long long row0 = (long long)blockIdx.x * T;
+    const int np = (int)min((long long)T, n - row0);
+    tile_zero_pads(L, b);
+    __syncthreads();
+    load_rows(b.zs, L.DP, eps, L.d, row0, np, T);
+    __syncthreads();
+    flow_sample<T>(L, b, f, blob, lq);
+    store_rows(x, L.d, b.zs, L.DP, row0, np);
+    for (int p = threadIdx.x; p < np; p += FAB_NT) log_q[row0 + p] = lq[p];
+}
+
+template <int T, bool GRAD>
+__global__ void __launch_bounds__(FAB_NT, 1)
+k_flow_logprob(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
+               const float* __restrict__ x, float* __restrict__ log_q, float* __restrict__ grad,
+               long long n) {
+    extern __shared__ __align__(16) float smem[];
+    const TileBufs b = tile_bufs(L, smem);
+    float* lq = smem + L.o_state;
+    const long long row0 = (long long)blockIdx.x * T;
+    const int np = (int)min((long long)T, n - row0);
+    tile_zero_pads(L, b);
+    __syncthreads();
+    load_rows(b.zs, L.DP, x, L.d, row0, np, T);
+    __syncthreads();
+    flow_inverse<T, GRAD>(L, b, f, blob, lq);
+    if (GRAD) {
+        flow_backward<T>(L, b, f, blob);
+        store_rows(grad, L.d, b.vs, L.DP, row0, np);
+    }
+    for (int p = threadIdx.x; p < np; p += FAB_NT) log_q[row0 + p] = lq[p];
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain initialisation (ais.py:56-65)
+// state area: x[T][DP], gq[T][DP], gp[T][DP], lq0[T], lq[T], lp[T]
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int init_state_floats(int T, int DP) { return 3 * T * DP + 3 * fab_round4(T); }
+
+template <int T, bool GRAD>
+__global__ void __launch_bounds__(FAB_NT, 1)
+k_ais_init(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
+           const float* __restrict__ eps, fab_gamma g1, fab_point out, float* __restrict__ log_w,
+           float* __restrict__ log_q0, uint8_t* __restrict__ valid, long long n) {
+    extern __shared__ __align__(16) float smem[];
+    const TileBufs b = tile_bufs(L, smem);
+    float* sx = smem + L.o_state;
+    float* sgq = sx + T * L.DP;
+    float* sgp = sgq + T * L.DP;
+    float* slq0 = sgp + T * L.DP;
+    float* slq = slq0 + fab_round4(T);
+    float* slp = slq + fab_round4(T);
+    const long long row0 = (long long)blockIdx.x * T;
+    const int np = (int)min((long long)T, n - row0);
+    tile_zero_pads(L, b);
+    __syncthreads();
+    load_rows(b.zs, L.DP, eps, L.d, row0, np, T);
+    __syncthreads();
+    flow_sample<T>(L, b, f, blob, slq0);
+    copy_tile(sx, b.zs, T * L.DP);
+    __syncthreads();
+    if (GRAD) {
+        // create_point(with_grad=True) re-evaluates log q by the inverse pass
+        eval_point<T, true>(L, b, f, blob, tgt, sx, slq, slp, sgq, sgp);
+    } else {
+        target_tile<T>(tgt, sx, L.DP, L.d, slp, nullptr);
+        for (int p = threadIdx.x; p < T; p += FAB_NT) slq[p] = slq0[p];
+        __syncthreads();
+    }
+    store_rows(out.d_x, L.d, sx, L.DP, row0, np);
+    if (GRAD) {
+        store_rows(out.d_grad_log_q, L.d, sgq, L.DP, row0, np);
+        store_rows(out.d_grad_log_p, L.d, sgp, L.DP, row0, np);
+    }
+    for (int p = threadIdx.x; p < np; p += FAB_NT) {
+        const float lq = slq[p], lp = slp[p], lq0 = slq0[p];
+        out.d_log_q[row0 + p] = lq;
+        out.d_log_p[row0 + p] = lp;
+        log_w[row0 + p] = __fsub_rn(gamma_of(g1, lq, lp), lq0);
+        if (log_q0) log_q0[row0 + p] = lq0;
+        valid[row0 + p] = (fab_isfinite(lq) && fab_isfinite(lp)) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic cross-CTA reduction: every CTA deposits `NV` floats, the last one to arrive sums
+// them in block order.  Workspace: float partial[grid][NV] followed by one uint32 counter, which
+// must be 0 on entry and is reset to 0 on exit.
+// Returns true (block-uniform) in the last CTA, with totals[NV] (shared) filled.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__device__ bool grid_reduce_last(const float* mine /*shared[NV]*/, float* ws, float* totals) {
+    __shared__ int s_last;
+    float* partial = ws;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)gridDim.x * NV);
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < NV; ++v) partial[(size_t)blockIdx.x * NV + v] = mine[v];
+        __threadfence();
+        const unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        for (int v = 0; v < NV; ++v) {
+            float s = 0.f;
+            for (unsigned int blk = threadIdx.x; blk < gridDim.x; blk += 32)
+                s += __ldcg(partial + (size_t)blk * NV + v);
+            s = warp_sum(s);
+            if (threadIdx.x == 0) totals[v] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+    __syncthreads();
+    return true;
+}
+
+// HMC tuner + logging scalars (hmc.py:157-183), executed by one thread.
+__device__ __forceinline__ void hmc_finish(const fab_hmc_state& st, const fab_hmc_args& a,
+                                           float sum_exp, float count, float dist_sum) {
+    const float log_mean = logf(sum_exp) - logf(count);
+    const float p_mean = expf(log_mean);
+    if (a.i == 1) {
+        st.d_log[a.outer] = p_mean;
+        st.d_log[2 * st.n_outer] = dist_sum / count;
+    } else if (a.i == st.n_dist) {
+        st.d_log[st.n_outer + a.outer] = p_mean;
+        st.d_log[2 * st.n_outer + 1] = dist_sum / count;
+    }
+    if (a.tune) {
+        float* e = st.d_epsilons + (size_t)(a.i - 1) * st.n_outer + a.outer;
+        if (log_mean > logf(a.target_p_accept)) {
+            *e = __fmul_rn(*e, 1.05f);
+            *st.d_common_epsilon = __fmul_rn(*st.d_common_epsilon, 1.02f);
+        } else {
+            *e = __fdiv_rn(*e, 1.05f);
+            *st.d_common_epsilon = __fdiv_rn(*st.d_common_epsilon, 1.02f);
+        }
+    }
+}
+
+__global__ void k_hmc_finish(fab_hmc_state st, fab_hmc_args a, const float* __restrict__ stats) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) hmc_finish(st, a, stats[0], stats[1], stats[2]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused HMC outer step (hmc.py:129-160)
+// state area: cur{x,gq,gp}, prop{x,gq,gp}, mom : 7*[T][DP]; scalars cur_lq,cur_lp,prop_lq,prop_lp,
+// ke0, red2[4]
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int hmc_state_floats(int T, int DP) { return 7 * T * DP + 8 * fab_round4(T) + 8; }
+
+template <int T>
+__global__ void __launch_bounds__(FAB_NT, 1)
+k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
+           fab_hmc_state st, fab_hmc_args a, fab_point cur, fab_point prop_in, fab_point prop_out,
+           float* __restrict__ log_w, const float* __restrict__ mom_noise,
+           const float* __restrict__ exp_noise, const int* __restrict__ n_active,
+           float* __restrict__ stats, float* ws, long long n) {
+    extern __shared__ __align__(16) float smem[];
+    const TileBufs b = tile_bufs(L, smem);
+    const int TD = T * L.DP, T4 = fab_round4(T);
+    float* cx = smem + L.o_state;
+    float* cgq = cx + TD;  float* cgp = cgq + TD;
+    float* px = cgp + TD;  float* pgq = px + TD;  float* pgp = pgq + TD;
+    float* mom = pgp + TD;
+    float* clq = mom + TD; float* clp = clq + T4;
+    float* plq = clp + T4; float* plp = plq + T4;
+    float* ke0 = plp + T4; float* acc_flag = ke0 + T4;
+    float* contrib = acc_flag + T4; float* moved = contrib + T4;
+    float* blk = moved + T4;             // [0]=sum exp(min(log_a,0)), [1]=sum dist, [4..]=totals
+
+    const long long n_act = n_active ? (long long)(*n_active) : n;
+    const long long row0 = (long long)blockIdx.x * T;
+    int np = (int)min((long long)T, n_act - row0);
+    if (np < 0) np = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (np > 0) {
+        tile_zero_pads(L, b);
+        load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
+        load_rows(cgq, L.DP, cur.d_grad_log_q, L.d, row0, np, T);
+        load_rows(cgp, L.DP, cur.d_grad_log_p, L.d, row0, np, T);
+        for (int p = threadIdx.x; p < T; p += FAB_NT) {
+            clq[p] = p < np ? cur.d_log_q[row0 + p] : 0.f;
+            clp[p] = p < np ? cur.d_log_p[row0 + p] : 0.f;
+        }
+        if (prop_in.d_x) {
+            load_rows(px, L.DP, prop_in.d_x, L.d, row0, np, T);
+            load_rows(pgq, L.DP, prop_in.d_grad_log_q, L.d, row0, np, T);
+            load_rows(pgp, L.DP, prop_in.d_grad_log_p, L.d, row0, np, T);
+            for (int p = threadIdx.x; p < T; p += FAB_NT) {
+                plq[p] = p < np ? prop_in.d_log_q[row0 + p] : 0.f;
+                plp[p] = p < np ? prop_in.d_log_p[row0 + p] : 0.f;
+            }
+        }
+        __syncthreads();
+        if (!prop_in.d_x) {
+            copy_tile(px, cx, TD); copy_tile(pgq, cgq, TD); copy_tile(pgp, cgp, TD);
+            for (int p = threadIdx.x; p < T; p += FAB_NT) { plq[p] = clq[p]; plp[p] = clp[p]; }
+        }
+        // step size eps(i, n) = epsilons[i-1, n] + common_epsilon   (hmc.py:90-100)
+        const float eps = __fadd_rn(st.d_epsilons[(size_t)(a.i - 1) * st.n_outer + a.outer],
+                                    st.d_common_epsilon[0]);
+        // momentum p0 = randn * mass  (hmc.py:134) and its kinetic energy sum(p^2/m)/2
+        for (int i = threadIdx.x; i < TD; i += FAB_NT) {
+            const int p = i / L.DP, j = i - p * L.DP;
+            mom[i] = (p < np && j < L.d)
+                         ? __fmul_rn(__ldg(mom_noise + (row0 + p) * L.d + j), __ldg(st.d_mass + j))
+                         : 0.f;
+        }
+        __syncthreads();
+        for (int p = warp; p < T; p += FAB_NWARPS) {
+            float s = 0.f;
+            for (int j = lane; j < L.d; j += 32) {
+                const float m = mom[p * L.DP + j];
+                s += __fdiv_rn(__fmul_rn(m, m), __ldg(st.d_mass + j));
+            }
+            s = warp_sum(s);
+            if (lane == 0) ke0[p] = 0.5f * s;
+        }
+        // leapfrog (hmc.py:138-147)
+        for (int l = 0; l < a.L; ++l) {
+            for (int i = threadIdx.x; i < TD; i += FAB_NT) {
+                const int j = i % L.DP;
+                if (j < L.d) {
+                    const float gu = grad_u_of(a.g, pgq[i], pgp[i], a.max_grad);
+                    const float m = __fsub_rn(mom[i], __fmul_rn(__fmul_rn(eps, gu), 0.5f));
+                    mom[i] = m;
+                    px[i] = __fadd_rn(px[i], __fmul_rn(__fdiv_rn(eps, __ldg(st.d_mass + j)), m));
+                }
+            }
+            __syncthreads();
+            eval_point<T, true>(L, b, f, blob, tgt, px, plq, plp, pgq, pgp);
+            for (int i = threadIdx.x; i < TD; i += FAB_NT) {
+                const int j = i % L.DP;
+                if (j < L.d) {
+                    const float gu = grad_u_of(a.g, pgq[i], pgp[i], a.max_grad);
+                    mom[i] = __fsub_rn(mom[i], __fmul_rn(__fmul_rn(eps, gu), 0.5f));
+                }
+            }
+            __syncthreads();
+        }
+        // Metropolis accept (hmc.py:105-124) + "distance moved" (hmc.py:173-183, measured against
+        // the already-overwritten current point: 0 for accepted particles)
+        if (threadIdx.x < 2) blk[threadIdx.x] = 0.f;
+        for (int p = warp; p < T; p += FAB_NWARPS) {
+            float s = 0.f, dd = 0.f;
+            for (int j = lane; j < L.d; j += 32) {
+                const float m = mom[p * L.DP + j];
+                s += __fdiv_rn(__fmul_rn(m, m), __ldg(st.d_mass + j));
+                const float df = cx[p * L.DP + j] - px[p * L.DP + j];
+                dd += df * df;
+            }
+            s = warp_sum(s);
+            dd = warp_sum(dd);
+            if (lane == 0) {
+                float flag = 0.f, c_p = 0.f, d_p = 0.f;
+                if (p < np) {
+                    const float lj_cur = __fsub_rn(gamma_of(a.g, clq[p], clp[p]), ke0[p]);
+                    const float lj_prop = __fsub_rn(gamma_of(a.g, plq[p], plp[p]), 0.5f * s);
+                    float log_a = __fsub_rn(lj_prop, lj_cur);
+                    const bool ok = fab_isfinite(log_a);
+                    if (!ok) log_a = -CUDART_INF_F;
+                    const bool acc = ok && (log_a > -__ldg(exp_noise + row0 + p));
+                    flag = acc ? 1.f : 0.f;
+                    // per-particle contributions; summed over p below in fixed order
+                    c_p = expf(fminf(log_a, 0.f));
+                    d_p = acc ? 0.f : sqrtf(dd);
+                }
+                acc_flag[p] = flag; contrib[p] = c_p; moved[p] = d_p;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f, dsum = 0.f;
+            for (int p = 0; p < np; ++p) { s += contrib[p]; dsum += moved[p]; }
+            blk[0] = s; blk[1] = dsum;
+        }
+        // overwrite accepted rows: cur[accept] = prop[accept]  (hmc.py:154)
+        for (int i = threadIdx.x; i < TD; i += FAB_NT) {
+            const int p = i / L.DP;
+            if (acc_flag[p] != 0.f) { cx[i] = px[i]; cgq[i] = pgq[i]; cgp[i] = pgp[i]; }
+        }
+        for (int p = threadIdx.x; p < T; p += FAB_NT)
+            if (acc_flag[p] != 0.f) { clq[p] = plq[p]; clp[p] = plp[p]; }
+        __syncthreads();
+        store_rows(cur.d_x, L.d, cx, L.DP, row0, np);
+        store_rows(cur.d_grad_log_q, L.d, cgq, L.DP, row0, np);
+        store_rows(cur.d_grad_log_p, L.d, cgp, L.DP, row0, np);
+        for (int p = threadIdx.x; p < np; p += FAB_NT) {
+            cur.d_log_q[row0 + p] = clq[p];
+            cur.d_log_p[row0 + p] = clp[p];
+            if (a.update_log_w) {   // ais.py:93-100
+                const float inc = __fsub_rn(gamma_of(a.g_next, clq[p], clp[p]),
+                                            gamma_of(a.g_w, clq[p], clp[p]));
+                log_w[row0 + p] = __fadd_rn(log_w[row0 + p], inc);
+            }
+        }
+        if (prop_out.d_x) {
+            store_rows(prop_out.d_x, L.d, px, L.DP, row0, np);
+            store_rows(prop_out.d_grad_log_q, L.d, pgq, L.DP, row0, np);
+            store_rows(prop_out.d_grad_log_p, L.d, pgp, L.DP, row0, np);
+            for (int p = threadIdx.x; p < np; p += FAB_NT) {
+                prop_out.d_log_q[row0 + p] = plq[p];
+                prop_out.d_log_p[row0 + p] = plp[p];
+            }
+        }
+    } else {
+        if (threadIdx.x < 2) blk[threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    if (grid_reduce_last<2>(blk, ws, blk + 4)) {
+        if (threadIdx.x == 0) {
+            stats[0] = blk[4]; stats[1] = (float)n_act; stats[2] = blk[5]; stats[3] = 0.f;
+            if (!a.defer_stats) hmc_finish(st, a, blk[4], (float)n_act, blk[5]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused Metropolis transition (metropolis.py:51-74): all n_updates in one launch
+// state area: cur x, prop x : 2*[T][DP]; scalars cur_lq,cur_lp,prop_lq,prop_lp,g_prev,flag;
+// blk[FAB_MAX_UPDATES*2]
+// ---------------------------------------------------------------------------------------------
+#define FAB_MAX_UPDATES 16
+__host__ __device__ inline int metro_state_floats(int T, int DP) {
+    return 2 * T * DP + 7 * fab_round4(T) + 4 * FAB_MAX_UPDATES;
+}
+
+__device__ __forceinline__ void metropolis_finish(const fab_metropolis_args& a, float* scal,
+                                                  int nu, float sum, float count) {
+    if (!a.tune) return;
+    float* s = scal + (size_t)(a.i - 1) * a.n_updates + nu;
+    const float p_acc = sum / count;
+    if (p_acc > a.target_p_accept) *s = __fmul_rn(*s, 1.05f);
+    else *s = __fdiv_rn(*s, 1.05f);
+}
+
+__global__ void k_metropolis_finish(fab_metropolis_args a, float* scal,
+                                    const float* __restrict__ stats) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        for (int u = 0; u < a.n_updates; ++u) metropolis_finish(a, scal, u, stats[2 * u], stats[2 * u + 1]);
+}
+
+template <int T>
+__global__ void __launch_bounds__(FAB_NT, 1)
+k_metropolis(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
+             fab_metropolis_args a, float* scal, fab_point cur, float* __restrict__ log_w,
+             const float* __restrict__ prop_noise, const float* __restrict__ unif,
+             const int* __restrict__ n_active, float* __restrict__ stats, float* ws, long long n) {
+    extern __shared__ __align__(16) float smem[];
+    const TileBufs b = tile_bufs(L, smem);
+    const int TD = T * L.DP, T4 = fab_round4(T);
+    float* cx = smem + L.o_state;
+    float* px = cx + TD;
+    float* clq = px + TD;  float* clp = clq + T4;
+    float* plq = clp + T4; float* plp = plq + T4;
+    float* gprev = plp + T4; float* flag = gprev + T4; float* contrib = flag + T4;
+    float* blk = contrib + T4;                    // [u] = sum_p min(a,1) ; totals at [2*MAXU + u]
+
+    const long long n_act = n_active ? (long long)(*n_active) : n;
+    const long long row0 = (long long)blockIdx.x * T;
+    int np = (int)min((long long)T, n_act - row0);
+    if (np < 0) np = 0;
+    for (int u = threadIdx.x; u < 4 * FAB_MAX_UPDATES; u += FAB_NT) blk[u] = 0.f;
+    if (np > 0) {
+        tile_zero_pads(L, b);
+        load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
+        for (int p = threadIdx.x; p < T; p += FAB_NT) {
+            const float lq = p < np ? cur.d_log_q[row0 + p] : 0.f;
+            const float lp = p < np ? cur.d_log_p[row0 + p] : 0.f;
+            clq[p] = lq; clp[p] = lp;
+            gprev[p] = gamma_of(a.g, lq, lp);     // never refreshed
+        }
+        __syncthreads();
+        for (int u = 0; u < a.n_updates; ++u) {
+            const float sigma = scal[(size_t)(a.i - 1) * a.n_updates + u];
+            const float* nz = prop_noise + (size_t)u * n * L.d;
+            for (int i = threadIdx.x; i < TD; i += FAB_NT) {
+                const int p = i / L.DP, j = i - p * L.DP;
+                px[i] = (p < np && j < L.d)
+                            ? __fadd_rn(cx[i], __fmul_rn(__ldg(nz + (row0 + p) * L.d + j), sigma))
+                            : 0.f;
+            }
+            __syncthreads();
+            eval_point<T, false>(L, b, f, blob, tgt, px, plq, plp, nullptr, nullptr);
+            if (threadIdx.x < T) {
+                const int p = threadIdx.x;
+                float fl = 0.f, c_p = 0.f;
+                if (p < np) {
+                    float acc = expf(__fsub_rn(gamma_of(a.g, plq[p], plp[p]), gprev[p]));
+                    if (!fab_isfinite(acc)) acc = 0.f;          // nan_to_num(nan=0, +-inf=0)
+                    fl = (acc > __ldg(unif + (size_t)u * n + row0 + p)) ? 1.f : 0.f;
+                    c_p = fminf(acc, 1.f);
+                }
+                flag[p] = fl; contrib[p] = c_p;
+                if (fl != 0.f) { clq[p] = plq[p]; clp[p] = plp[p]; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float s = 0.f;
+                for (int p = 0; p < np; ++p) s += contrib[p];
+                blk[u] = s;
+            }
+            for (int i = threadIdx.x; i < TD; i += FAB_NT) {
+                const int p = i / L.DP;
+                if (flag[p] != 0.f) cx[i] = px[i];
+            }
+            __syncthreads();
+        }
+        store_rows(cur.d_x, L.d, cx, L.DP, row0, np);
+        for (int p = threadIdx.x; p < np; p += FAB_NT) {
+            cur.d_log_q[row0 + p] = clq[p];
+            cur.d_log_p[row0 + p] = clp[p];
+            if (a.update_log_w) {
+                const float inc = __fsub_rn(gamma_of(a.g_next, clq[p], clp[p]),
+                                            gamma_of(a.g_w, clq[p], clp[p]));
+                log_w[row0 + p] = __fadd_rn(log_w[row0 + p], inc);
+            }
+        }
+    }
+    __syncthreads();
+    if (grid_reduce_last<FAB_MAX_UPDATES>(blk, ws, blk + 2 * FAB_MAX_UPDATES)) {
+        if (threadIdx.x == 0) {
+            for (int u = 0; u < a.n_updates; ++u) {
+                stats[2 * u] = blk[2 * FAB_MAX_UPDATES + u];
+                stats[2 * u + 1] = (float)n_act;
+                if (!a.defer_stats)
+                    metropolis_finish(a, scal, u, blk[2 * FAB_MAX_UPDATES + u], (float)n_act);
+            }
+        }
+    }
+}

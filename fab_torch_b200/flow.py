@@ -1,0 +1,365 @@
+"""B200RealNVP: the reference's RealNVP-style coupling flow behind the `TrainableDistribution`
+surface (fab/wrappers/normflows.py:8-31), evaluated by the sm_100a tile kernels.
+
+Architecture = experiments/make_flow/make_normflow_model.py:11-30,82-96 (normflows):
+DiagGaussian base, then per layer AffineCouplingBlock(MLP[d1, W, W, 2*d2], exp scale) followed by
+an LU-parameterised InvertibleAffine.  Parameter/module names follow normflows so checkpoints
+written by `FABModel.save` (fab/core.py:222-260) keep the reference's state-dict keys
+(`_nf_model.q0.loc`, `_nf_model.flows.0.flows.1.param_map.net.0.weight`,
+`_nf_model.flows.1.{P,L,U,log_S,sign_S,eye}`), and default initialisation consumes the torch RNG
+in the same order as normflows (so `torch.manual_seed(s)` gives the same weights).
+
+Hot path: `sample_and_log_prob`, `log_prob` and d log_prob / dx run as CUDA kernels on a packed
+weight blob (layout: include/fab_b200.h) that is rebuilt lazily whenever a parameter changes.
+Gradients w.r.t. the flow parameters (needed only by the training loss, fab/core.py:112-118 --
+SURVEY §8f row 2, outside the sampler) are produced by re-evaluating the same maths with torch
+ops on the GPU inside `backward`.
+"""
+import math
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from fab_torch_b200 import _lib
+from fab_torch_b200.types_ import TrainableDistribution
+
+
+# --------------------------------------------------------------------------- parameter containers
+class _DiagGaussian(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.shape = (dim,)
+        self.loc = nn.Parameter(torch.zeros(1, dim))
+        self.log_scale = nn.Parameter(torch.zeros(1, dim))
+
+
+class _MLP(nn.Module):
+    def __init__(self, sizes, init_zeros=True):
+        super().__init__()
+        mods = []
+        for a, b in zip(sizes[:-2], sizes[1:-1]):
+            mods += [nn.Linear(a, b), nn.LeakyReLU(0.0)]
+        mods.append(nn.Linear(sizes[-2], sizes[-1]))
+        if init_zeros:
+            nn.init.zeros_(mods[-1].weight)
+            nn.init.zeros_(mods[-1].bias)
+        self.net = nn.Sequential(*mods)
+
+
+class _AffineCoupling(nn.Module):
+    def __init__(self, param_map):
+        super().__init__()
+        self.add_module("param_map", param_map)
+
+
+class _CouplingBlock(nn.Module):
+    """flows[1] holds the conditioner, like normflows' [Split, AffineCoupling, Merge]."""
+
+    def __init__(self, param_map):
+        super().__init__()
+        self.flows = nn.ModuleList([nn.Identity(), _AffineCoupling(param_map), nn.Identity()])
+
+    @property
+    def linears(self):
+        net = self.flows[1].param_map.net
+        return net[0], net[2], net[4]
+
+
+class _InvertibleAffine(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        Q, _ = torch.linalg.qr(torch.randn(dim, dim))
+        LU, piv = torch.linalg.lu_factor(Q)
+        P, L, U = torch.lu_unpack(LU, piv)
+        self.register_buffer("P", P)
+        self.L = nn.Parameter(L)
+        S = U.diag()
+        self.register_buffer("sign_S", torch.sign(S))
+        self.log_S = nn.Parameter(torch.log(torch.abs(S)))
+        self.U = nn.Parameter(torch.triu(U, diagonal=1))
+        self.register_buffer("eye", torch.diag(torch.ones(dim)))
+
+
+class _NFModel(nn.Module):
+    def __init__(self, dim, n_layers, width):
+        super().__init__()
+        self.q0 = _DiagGaussian(dim)
+        d1 = int((dim / 2) + 0.5)
+        flows = []
+        for _ in range(n_layers):
+            flows.append(_CouplingBlock(_MLP([d1, width, width, 2 * (dim - d1)])))
+            flows.append(_InvertibleAffine(dim))
+        self.flows = nn.ModuleList(flows)
+
+
+# --------------------------------------------------------------------------- packing helpers
+def _r4(v: int) -> int:
+    return (v + 3) // 4 * 4
+
+
+def _pack_operand(M: torch.Tensor, Kpad: int, NP: int) -> torch.Tensor:
+    """M [Lyr, K, N] -> packed float4 operand [Lyr, Kpad/4 * NP * 4] (see include/fab_b200.h)."""
+    Lyr, K, N = M.shape
+    out = M.new_zeros(Lyr, Kpad, NP)
+    out[:, :K, :N] = M
+    return out.view(Lyr, Kpad // 4, 4, NP).permute(0, 1, 3, 2).reshape(Lyr, -1)
+
+
+def _pad_last(v: torch.Tensor, n: int) -> torch.Tensor:
+    out = v.new_zeros(*v.shape[:-1], n)
+    out[..., :v.shape[-1]] = v
+    return out
+
+
+class B200RealNVP(TrainableDistribution):
+    """Drop-in for `make_wrapped_normflow_realnvp(dim, n_flow_layers, layer_nodes_per_dim,
+    act_norm=False)` (make_normflow_model.py:82-96)."""
+
+    def __init__(self, dim: int, n_flow_layers: int = 5, layer_nodes_per_dim: int = 10,
+                 act_norm: bool = False):
+        super().__init__()
+        if act_norm:
+            raise NotImplementedError(
+                "act_norm=True is not supported by the B200 path (every shipped reference config "
+                "sets flow.act_norm: false)")
+        self.dim = dim
+        self.n_flow_layers = n_flow_layers
+        self.width = dim * layer_nodes_per_dim
+        self._nf_model = _NFModel(dim, n_flow_layers, self.width)
+        self._desc = _lib.FlowDesc()
+        self._blob = None
+        self._blob_key = None
+        self._eps_override = None       # test hook: next sample uses this base noise
+        # filled lazily: needs the .so
+        self._desc_ready = False
+
+    # ---- descriptor / blob -------------------------------------------------------------
+    def desc(self) -> "_lib.FlowDesc":
+        if not self._desc_ready:
+            n = _lib.lib().fab_flow_desc_init(self._desc, self.dim, max(self.width, 1),
+                                              self.n_flow_layers)
+            _lib.check(n, "fab_flow_desc_init")
+            self._desc_ready = True
+        return self._desc
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def blob(self) -> torch.Tensor:
+        """Packed fp32 weights on the parameters' device, rebuilt only when a parameter changed."""
+        key = self._param_key()
+        if self._blob is None or key != self._blob_key:
+            with torch.no_grad():
+                self._blob = self._pack()
+            self._blob_key = key
+        return self._blob
+
+    def _mixing(self, dtype=torch.float32):
+        """Stacked W, W^-1 [K,d,d] and sum(log_S) [K], assembled exactly like normflows'
+        InvertibleAffine._assemble_W (inverse of L and U in float64, then cast)."""
+        mixes = [self._nf_model.flows[2 * k + 1] for k in range(self.n_flow_layers)]
+        P = torch.stack([m.P for m in mixes])
+        eye = mixes[0].eye
+        L = torch.tril(torch.stack([m.L for m in mixes]), diagonal=-1) + eye
+        log_S = torch.stack([m.log_S for m in mixes])
+        sign_S = torch.stack([m.sign_S for m in mixes])
+        U = torch.triu(torch.stack([m.U for m in mixes]), diagonal=1) + \
+            torch.diag_embed(sign_S * torch.exp(log_S))
+        W = P @ L @ U
+        L_inv = torch.inverse(L.double()).to(dtype)
+        U_inv = torch.inverse(U.double()).to(dtype)
+        W_inv = U_inv @ L_inv @ P.transpose(1, 2)
+        return W, W_inv, log_S.sum(dim=1)
+
+    def _pack(self) -> torch.Tensor:
+        d = self.desc()
+        dev = self._nf_model.q0.loc.device
+        if self._nf_model.q0.loc.dtype != torch.float32:
+            raise RuntimeError("B200RealNVP kernels are fp32; keep the flow in float32")
+        DP, D1P, P2, WP = _r4(d.dim), _r4(d.d1), _r4(2 * d.d2), d.width_pad
+        base = torch.cat([_pad_last(self._nf_model.q0.loc.reshape(-1), DP),
+                          _pad_last(self._nf_model.q0.log_scale.reshape(-1), DP)])
+        K = self.n_flow_layers
+        if K == 0:
+            return base.contiguous()
+        blocks = [self._nf_model.flows[2 * k] for k in range(K)]
+        W1 = torch.stack([b.linears[0].weight for b in blocks])     # [K, W, d1]
+        b1 = torch.stack([b.linears[0].bias for b in blocks])
+        W2 = torch.stack([b.linears[1].weight for b in blocks])     # [K, W, W]
+        b2 = torch.stack([b.linears[1].bias for b in blocks])
+        W3 = torch.stack([b.linears[2].weight for b in blocks])     # [K, 2*d2, W]
+        b3 = torch.stack([b.linears[2].bias for b in blocks])
+        perm = torch.cat([torch.arange(0, 2 * d.d2, 2), torch.arange(1, 2 * d.d2, 2)]).to(dev)
+        W3 = W3[:, perm, :]
+        b3 = b3[:, perm]
+        Wm, Wm_inv, logs = self._mixing()
+        t = lambda M: M.transpose(1, 2)
+        parts = [
+            _pack_operand(Wm, DP, DP),                 # o_mix     M[k][n] = W[k][n]
+            _pack_operand(t(Wm), DP, DP),              # o_mix_t   M[k][n] = W[n][k]
+            _pack_operand(Wm_inv, DP, DP),             # o_mix_inv
+            _pack_operand(t(W1), D1P, WP),             # o_w1      M[k][n] = W1[n][k]
+            _pack_operand(t(W2), WP, WP),              # o_w2
+            _pack_operand(t(W3), WP, P2),              # o_w3
+            _pack_operand(W3, P2, WP),                 # o_w3t     M[k][n] = W3p[k][n]
+            _pack_operand(W2, WP, WP),                 # o_w2t
+            _pack_operand(W1, WP, D1P),                # o_w1t
+            _pad_last(b1, WP), _pad_last(b2, WP), _pad_last(b3, P2),
+            _pad_last(logs[:, None], 4),
+        ]
+        layers = torch.cat(parts, dim=1)
+        assert layers.shape[1] == d.layer_stride, (layers.shape, d.layer_stride)
+        blob = torch.cat([base, layers.reshape(-1)]).contiguous()
+        assert blob.numel() == d.total_floats
+        return blob
+
+    # ---- Distribution surface ----------------------------------------------------------------
+    @property
+    def event_shape(self) -> Tuple[int, ...]:
+        return self._nf_model.q0.shape
+
+    def _device(self):
+        return self._nf_model.q0.loc.device
+
+    def sample_and_log_prob(self, shape: Tuple[int, ...]) -> Tuple[torch.Tensor, torch.Tensor]:
+        assert len(shape) == 1
+        eps, self._eps_override = self._eps_override, None
+        if eps is None:
+            eps = torch.randn((shape[0], self.dim), dtype=torch.float32, device=self._device())
+        return _SampleFn.apply(self, eps, *self.parameters())
+
+    def sample(self, shape: Tuple) -> torch.Tensor:
+        return self.sample_and_log_prob(shape)[0]
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        return _LogProbFn.apply(self, x, *self.parameters())
+
+    # raw kernel launches (no autograd), used by the fused sampler too
+    def cuda_sample(self, eps: torch.Tensor):
+        eps = _lib.f32(eps).contiguous()
+        n = eps.shape[0]
+        x = torch.empty_like(eps)
+        log_q = torch.empty(n, dtype=torch.float32, device=eps.device)
+        rc = _lib.lib().fab_flow_sample_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(eps),
+                                            _lib.ptr(x), _lib.ptr(log_q), n,
+                                            _lib.stream_ptr(eps.device))
+        _lib.check(rc, "fab_flow_sample_f32")
+        return x, log_q
+
+    def cuda_log_prob(self, x: torch.Tensor, with_grad: bool):
+        x = _lib.f32(x).contiguous()
+        n = x.shape[0]
+        log_q = torch.empty(n, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if with_grad else None
+        rc = _lib.lib().fab_flow_logprob_grad_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(x),
+                                                  _lib.ptr(log_q), _lib.ptr(grad), n,
+                                                  _lib.stream_ptr(x.device))
+        _lib.check(rc, "fab_flow_logprob_grad_f32")
+        return log_q, grad
+
+    # ---- the same maths in torch ops (GPU), differentiable w.r.t. parameters -----------------
+    def _coupling_params(self, k, v1):
+        l1, l2, l3 = self._nf_model.flows[2 * k].linears
+        h = torch.relu(l1(v1))
+        h = torch.relu(l2(h))
+        par = l3(h)
+        return par[:, 0::2], par[:, 1::2]
+
+    def torch_log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        d1 = int((self.dim / 2) + 0.5)
+        q0 = self._nf_model.q0
+        log_q = torch.zeros(len(x), dtype=x.dtype, device=x.device)
+        z = x
+        if self.n_flow_layers:
+            W, _, logs = self._mixing(x.dtype)
+        for k in range(self.n_flow_layers - 1, -1, -1):
+            v = z @ W[k]
+            v1, v2 = v[:, :d1], v[:, d1:]
+            shift, scale = self._coupling_params(k, v1)
+            z = torch.cat([v1, (v2 - shift) * torch.exp(-scale)], dim=1)
+            log_q = log_q + logs[k] - scale.sum(dim=1)
+        return log_q - 0.5 * self.dim * math.log(2 * math.pi) - torch.sum(
+            q0.log_scale + 0.5 * ((z - q0.loc) / torch.exp(q0.log_scale)) ** 2, dim=1)
+
+    def torch_sample(self, eps: torch.Tensor):
+        d1 = int((self.dim / 2) + 0.5)
+        q0 = self._nf_model.q0
+        z = q0.loc + torch.exp(q0.log_scale) * eps
+        log_q = -0.5 * self.dim * math.log(2 * math.pi) - torch.sum(
+            q0.log_scale + 0.5 * eps ** 2, dim=1)
+        if self.n_flow_layers:
+            _, W_inv, logs = self._mixing(eps.dtype)
+        for k in range(self.n_flow_layers):
+            v1, v2 = z[:, :d1], z[:, d1:]
+            shift, scale = self._coupling_params(k, v1)
+            z = torch.cat([v1, v2 * torch.exp(scale) + shift], dim=1) @ W_inv[k]
+            log_q = log_q - scale.sum(dim=1) + logs[k]
+        return z, log_q
+
+
+class _LogProbFn(torch.autograd.Function):
+    """forward: CUDA value + input-gradient; backward: dx from the saved input-gradient, dtheta (only
+    if some parameter requires grad) by re-running the torch-op restatement."""
+
+    @staticmethod
+    def forward(ctx, flow: B200RealNVP, x, *params):
+        need_dx = x.requires_grad
+        log_q, grad = flow.cuda_log_prob(x.detach(), with_grad=need_dx)
+        ctx.flow = flow
+        ctx.n_params = len(params)
+        ctx.save_for_backward(x.detach(), grad if grad is not None else x.new_empty(0))
+        ctx.has_dx = need_dx
+        return log_q
+
+    @staticmethod
+    def backward(ctx, g):
+        x, grad = ctx.saved_tensors
+        flow = ctx.flow
+        dx = g[:, None] * grad if (ctx.has_dx and ctx.needs_input_grad[1]) else None
+        dparams = [None] * ctx.n_params
+        if any(ctx.needs_input_grad[2:]):
+            with torch.enable_grad():
+                params = [p for p in flow.parameters()]
+                wanted = [p for p, need in zip(params, ctx.needs_input_grad[2:]) if need]
+                lq = flow.torch_log_prob(x)
+                gs = torch.autograd.grad(lq, wanted, grad_outputs=g, allow_unused=True)
+            it = iter(gs)
+            dparams = [next(it) if need else None for need in ctx.needs_input_grad[2:]]
+        return (None, dx, *dparams)
+
+
+class _SampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow: B200RealNVP, eps, *params):
+        x, log_q = flow.cuda_sample(eps)
+        ctx.flow = flow
+        ctx.n_params = len(params)
+        ctx.save_for_backward(eps)
+        return x, log_q
+
+    @staticmethod
+    def backward(ctx, gx, glq):
+        (eps,) = ctx.saved_tensors
+        flow = ctx.flow
+        dparams = [None] * ctx.n_params
+        if any(ctx.needs_input_grad[2:]):
+            with torch.enable_grad():
+                params = [p for p in flow.parameters()]
+                wanted = [p for p, need in zip(params, ctx.needs_input_grad[2:]) if need]
+                x, lq = flow.torch_sample(eps)
+                outs, gouts = [], []
+                if gx is not None:
+                    outs.append(x); gouts.append(gx)
+                if glq is not None:
+                    outs.append(lq); gouts.append(glq)
+                gs = torch.autograd.grad(outs, wanted, grad_outputs=gouts, allow_unused=True)
+            it = iter(gs)
+            dparams = [next(it) if need else None for need in ctx.needs_input_grad[2:]]
+        return (None, None, *dparams)
+
+
+def make_wrapped_b200_realnvp(dim: int, n_flow_layers: int = 5, layer_nodes_per_dim: int = 10,
+                              act_norm: bool = False) -> B200RealNVP:
+    """Same signature as `make_wrapped_normflow_realnvp` (make_normflow_model.py:82-96)."""
+    return B200RealNVP(dim, n_flow_layers, layer_nodes_per_dim, act_norm)

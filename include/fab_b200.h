@@ -1,0 +1,250 @@
+/*
+ * fab_b200.h -- C ABI of the B200-native AIS hot path (libfab_b200.so).
+ *
+ * The reference (lollcat/fab-torch) is pure Python and has no FFI of its own; its plugin
+ * boundary is the duck-typed Python surface
+ *     Distribution / TrainableDistribution   fab/types_.py:8-27, fab/trainable_distributions/base.py:4
+ *     TransitionOperator                     fab/sampling_methods/transition_operators/base.py:12-85
+ *     AnnealedImportanceSampler              fab/sampling_methods/ais.py:20-213
+ *     Point                                  fab/sampling_methods/base.py:7-47
+ * The Python classes in fab_torch_b200/ mirror that surface and bind the entry points below
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer; fp32, row-major, contiguous.
+ *   - desc structs are HOST pointers, read synchronously at call time.
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*): it never
+ *     synchronises, never allocates device memory, never throws.  Return value 0 = ok,
+ *     negative = FAB_E_* below; fab_last_error() gives a message for the calling thread.
+ *   - workspaces are caller-owned; sizes come from the *_workspace_bytes queries.
+ */
+#ifndef FAB_B200_H
+#define FAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAB_OK              0
+#define FAB_E_INVALID      -1   /* bad argument / unsupported shape            */
+#define FAB_E_CUDA         -2   /* a CUDA runtime call failed (launch config…) */
+#define FAB_E_UNSUPPORTED  -3   /* feature not compiled in                     */
+
+#define FAB_TARGET_MANYWELL 0
+#define FAB_TARGET_GMM      1
+
+/* ---------------------------------------------------------------------------------------
+ * Packed RealNVP parameters ("flow blob").
+ *
+ * Architecture = the one the reference builds in experiments/make_flow/make_normflow_model.py
+ * :11-30,82-96 with act_norm=False:  DiagGaussian base, then n_layers x { AffineCouplingBlock(
+ * MLP[d1 -> W -> W -> 2*d2], exp scale map), InvertibleAffine(d) }.
+ *
+ * Every dense matrix is stored as a "packed operand" for out[p][n] = sum_k act[p][k] * M[k][n]:
+ *      float4 Wp[K4][NP];   Wp[k4][n].{x,y,z,w} = M[4*k4 + {0,1,2,3}][n]    (0 beyond K or N)
+ *      K4 = ceil(K/4), NP = round_up(N, 4)
+ * so that consecutive threads (consecutive n) read consecutive 16-byte words.
+ * The hidden width is padded to WP = round_up(W, 4) with zero weights/biases.
+ *
+ * Blob layout (float offsets):  [base block][layer 0 block][layer 1 block]...
+ *   base block : loc[DP], log_scale[DP]                         DP = round_up(d,4)
+ *   layer block (all offsets relative to the layer block start; layer k of the reference's
+ *   flow list, k = 0 is applied first when sampling):
+ *     o_mix     packed  M[k][n] = Wmix[k][n]        K=d  N=d    inverse direction  z @ W
+ *     o_mix_t   packed  M[k][n] = Wmix[n][k]        K=d  N=d    gradient           g @ W^T
+ *     o_mix_inv packed  M[k][n] = Wmix^-1[k][n]     K=d  N=d    sampling direction z @ W^-1
+ *     o_w1      packed  M[k][n] = W1[n][k]          K=d1 N=WP   (nn.Linear weight is [out,in])
+ *     o_w2      packed  M[k][n] = W2[n][k]          K=WP N=WP
+ *     o_w3      packed  M[k][n] = W3[perm(n)][k]    K=WP N=2*d2  columns de-interleaved:
+ *                                                   n <  d2 -> shift row 2n, n >= d2 -> scale row 2(n-d2)+1
+ *     o_w3t     packed  M[k][n] = W3[perm(k)][n]    K=2*d2 N=WP
+ *     o_w2t     packed  M[k][n] = W2[k][n]          K=WP N=WP
+ *     o_w1t     packed  M[k][n] = W1[k][n]          K=WP N=d1
+ *     o_b1[WP], o_b2[WP], o_b3[P2] (de-interleaved like o_w3; P2 = round_up(2*d2,4))
+ *     o_logs[4] : [0] = sum(log_S) of this layer's InvertibleAffine
+ * ------------------------------------------------------------------------------------- */
+typedef struct fab_flow_desc {
+    int32_t dim;          /* d                                   */
+    int32_t d1;           /* int(d/2 + 0.5): conditioner input   */
+    int32_t d2;           /* d - d1: transformed half            */
+    int32_t width;        /* W  (as given by the caller)         */
+    int32_t width_pad;    /* WP = round_up(W,4)                  */
+    int32_t n_layers;     /* coupling blocks; 0 = plain diagonal Gaussian */
+    int64_t total_floats; /* blob size                           */
+    int64_t off_base_loc, off_base_log_scale;
+    int64_t off_layers, layer_stride;
+    int64_t o_mix, o_mix_t, o_mix_inv;
+    int64_t o_w1, o_w2, o_w3, o_w3t, o_w2t, o_w1t;
+    int64_t o_b1, o_b2, o_b3, o_logs;
+} fab_flow_desc;
+
+/* Fills every field of *desc from (dim, width, n_layers); returns total_floats or <0. */
+int64_t fab_flow_desc_init(fab_flow_desc* desc, int32_t dim, int32_t width, int32_t n_layers);
+
+/* ---------------------------------------------------------------------------------------
+ * Targets (fab/target_distributions/many_well.py:81-90 + double_well.py:44-58; gmm.py:44-66)
+ * ------------------------------------------------------------------------------------- */
+typedef struct fab_target_desc {
+    int32_t kind;             /* FAB_TARGET_*                                            */
+    int32_t dim;
+    int32_t n_mixes;          /* GMM                                                     */
+    int32_t mask_below_1e4;   /* GMM: log_prob < -1e4 -> -inf (gmm.py:63-65)             */
+    float   a, b, c;          /* many-well: E = a x1 + b x1^2 + c x1^4 + x2^2/2 per pair */
+    float   log_norm;         /* subtracted from log_prob (log Z if `normalised`, else 0)*/
+    const float* d_locs;      /* GMM [n_mixes, dim]                                      */
+    const float* d_scales;    /* GMM [n_mixes, dim] diagonal of scale_tril               */
+    const float* d_log_weights; /* GMM [n_mixes] log mixture weights (normalised)        */
+} fab_target_desc;
+
+/* Interpolation gamma(x) = cq*log_q + cp*log_p and grad = gq_c*grad_log_q + gp_c*grad_log_p
+ * (fab/sampling_methods/base.py:76-118).  The host computes the four coefficients in float64
+ * exactly as the reference does (incl. the literal `2*beta`, base.py:116) and rounds to fp32. */
+typedef struct fab_gamma {
+    float cq, cp;     /* density coefficients   */
+    float gq, gp;     /* gradient coefficients  */
+} fab_gamma;
+
+int  fab_version(void);
+const char* fab_last_error(void);
+/* Number of particles one thread block carries for a batch of n (dispatch heuristic). */
+int  fab_tile_particles(const fab_flow_desc* flow, int64_t n);
+
+/* K1/K2: eps[n,d] -> x[n,d], log_q[n]     (normflows NormalizingFlow.sample via
+ * fab/wrappers/normflows.py:16-18) */
+int fab_flow_sample_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_eps,
+                        float* d_x, float* d_log_q, int64_t n, void* stream);
+
+/* K3/K4: x[n,d] -> log_q[n] and (if d_grad != NULL) d log_q / d x [n,d]
+ * (fab/wrappers/normflows.py:23-24 + torch.autograd.grad in fab/sampling_methods/base.py:50-56) */
+int fab_flow_logprob_grad_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_x,
+                              float* d_log_q, float* d_grad, int64_t n, void* stream);
+
+/* K5/K15: x[n,d] -> log_p[n] and (if d_grad != NULL) its closed-form gradient */
+int fab_target_logprob_grad_f32(const fab_target_desc* target, const float* d_x,
+                                float* d_log_p, float* d_grad, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Chain state ("Point", fab/sampling_methods/base.py:7-47) as struct-of-arrays.
+ * grad_* may be NULL for value-only operators (Metropolis).
+ * ------------------------------------------------------------------------------------- */
+typedef struct fab_point {
+    float* d_x;           /* [n,d] */
+    float* d_log_q;       /* [n]   */
+    float* d_log_p;       /* [n]   */
+    float* d_grad_log_q;  /* [n,d] or NULL */
+    float* d_grad_log_p;  /* [n,d] or NULL */
+} fab_point;
+
+/* Chain initialisation, ais.py:56-65: sample the flow from eps, build the Point (value+grad of
+ * log q by the inverse pass when with_grad, else log_q := forward-pass log_q0), target value
+ * (+grad), log_w = gamma_1(point) - log_q0, valid[i] = isfinite(log_p) && isfinite(log_q).
+ * d_log_q0 (nullable) receives the forward-pass log q. */
+int fab_ais_init_f32(const fab_flow_desc* flow, const float* d_blob, const fab_target_desc* target,
+                     const float* d_eps, fab_gamma g1, int32_t with_grad,
+                     fab_point out, float* d_log_w, float* d_log_q0, uint8_t* d_valid,
+                     int64_t n, void* stream);
+
+/* HMC state that lives on the device (hmc.py:36-39 registered buffers + logging scalars). */
+typedef struct fab_hmc_state {
+    float* d_epsilons;        /* [M, n_outer]   per-distribution step sizes            */
+    float* d_common_epsilon;  /* [1]            shared step-size component             */
+    const float* d_mass;      /* [d]            mass vector                            */
+    float* d_log;             /* [4*n_outer + 2]: first_p_accept[n_outer], last_p_accept[n_outer],
+                                 avg_dist_first, avg_dist_last, spare...               */
+    int32_t n_dist;           /* M                                                     */
+    int32_t n_outer;
+} fab_hmc_state;
+
+typedef struct fab_hmc_args {
+    int32_t i;               /* intermediate distribution index, 1..M (hmc.py:186)     */
+    int32_t outer;           /* which outer step n this launch performs                */
+    int32_t L;               /* leapfrog steps                                         */
+    int32_t tune;            /* !eval_mode: apply adjust_step_size_p_accept (hmc.py:162-170) */
+    float   target_p_accept;
+    float   max_grad;        /* clamp for grad U (hmc.py:194-199)                      */
+    fab_gamma g;             /* gamma at beta_i                                        */
+    int32_t update_log_w;    /* after the accept: log_w += g_next(x) - g_w(x) (ais.py:93-100) */
+    fab_gamma g_w;           /* the SAMPLER's gamma at beta_i (its alpha/p_target may differ
+                                from the operator's, ais.py:94-98 vs hmc.py:188-191)   */
+    fab_gamma g_next;        /* the sampler's gamma at beta_{i+1}                      */
+    int32_t defer_stats;     /* 1: only write the local (sum_exp, count, dist) triple to d_stats
+                                and leave tuner/logging to fab_hmc_finish_f32 (multi-GPU)     */
+} fab_hmc_args;
+
+int64_t fab_hmc_workspace_bytes(const fab_flow_desc* flow, int64_t n);
+
+/* One HMC outer step (momentum draw .. accept/overwrite .. tuner) for all n particles, fused in
+ * one launch: hmc.py:129-160.  `cur` is updated in place.  For n_outer>1 the reference carries
+ * the *proposal* into the next outer step: pass prop_in = previous prop_out
+ * (NULL d_x = start from cur) and a prop_out buffer (NULL d_x = discard).
+ * d_mom_noise [n,d] ~ N(0,1), d_exp_noise [n] ~ Exp(1).  d_n_active (nullable) = device count of
+ * live particles (<= n) after an on-device NaN filter. */
+int fab_hmc_step_f32(const fab_flow_desc* flow, const float* d_blob, const fab_target_desc* target,
+                     fab_hmc_state st, fab_hmc_args args,
+                     fab_point cur, fab_point prop_in, fab_point prop_out,
+                     float* d_log_w, const float* d_mom_noise, const float* d_exp_noise,
+                     const int32_t* d_n_active, float* d_stats /* [4] */,
+                     void* d_workspace, int64_t n, void* stream);
+
+/* Multi-GPU tail of an outer step: d_stats holds the all-reduced (sum_exp, count, dist_sum). */
+int fab_hmc_finish_f32(fab_hmc_state st, fab_hmc_args args, const float* d_stats, void* stream);
+
+/* Metropolis (metropolis.py:51-74): all n_updates of one transition in one launch. */
+typedef struct fab_metropolis_args {
+    int32_t i;               /* 1..M                                                   */
+    int32_t n_updates;
+    int32_t tune;            /* adjust_step_size && !eval_mode                         */
+    float   target_p_accept;
+    fab_gamma g;
+    int32_t update_log_w;
+    fab_gamma g_w;           /* sampler's gamma at beta_i / beta_{i+1}, as in fab_hmc_args */
+    fab_gamma g_next;
+    int32_t defer_stats;
+} fab_metropolis_args;
+
+int64_t fab_metropolis_workspace_bytes(const fab_flow_desc* flow, int64_t n, int32_t n_updates);
+
+/* d_noise_scalings [M, n_updates] (updated in place when tuning), d_prop_noise [n_updates,n,d],
+ * d_unif [n_updates,n], d_stats [2*n_updates] = per update (sum min(a,1), count). */
+int fab_metropolis_transition_f32(const fab_flow_desc* flow, const float* d_blob,
+                                  const fab_target_desc* target, fab_metropolis_args args,
+                                  float* d_noise_scalings, fab_point cur, float* d_log_w,
+                                  const float* d_prop_noise, const float* d_unif,
+                                  const int32_t* d_n_active, float* d_stats,
+                                  void* d_workspace, int64_t n, void* stream);
+int fab_metropolis_finish_f32(fab_metropolis_args args, float* d_noise_scalings,
+                              const float* d_stats, void* stream);
+
+/* K11 alone (operator-level insertion keeps the reference's own loop): log_w += gn(x) - g(x). */
+int fab_logw_update_f32(fab_gamma g, fab_gamma g_next, const float* d_log_q, const float* d_log_p,
+                        float* d_log_w, int64_t n, void* stream);
+
+/* K12 (ais.py:190-213): stable compaction of the Point + log_w + any extra [n] / [n,d] rows by
+ * valid[i] = isfinite(log_p[i]) && isfinite(log_q[i]); writes the live count to d_n_out.
+ * In place; a no-op copy when everything is valid. */
+int64_t fab_filter_workspace_bytes(int64_t n, int32_t dim);
+int fab_nan_filter_f32(fab_point pt, float* d_log_w, int32_t dim, int64_t n,
+                       const int32_t* d_n_in, int32_t* d_n_out, void* d_workspace, void* stream);
+
+/* K13 (numerical.py:18-23, ais.py:80-86): partial = (max, sum e^(lw-max), sum e^(2(lw-max)), count)
+ * over this rank's live particles; finalize combines n_parts such quadruples (one per rank after
+ * an all-gather) into out[0]=ESS, out[1]=logsumexp(log_w), out[2]=total count. */
+int fab_ess_partial_f32(const float* d_log_w, const float* d_sub /* nullable: uses lw - sub */,
+                        int64_t n, const int32_t* d_n_active, float* d_partial4, void* stream);
+int fab_ess_finalize_f32(const float* d_partials4, int32_t n_parts, float* d_out3, void* stream);
+
+/* R (build extension, oracle/resample.py): systematic resampling with a fixed-point CDF.
+ * d_anc[n] = ancestor index for position (k + u0/2^32)/n.  Bit-exact vs the oracle. */
+int64_t fab_resample_workspace_bytes(int64_t n);
+int fab_resample_systematic_u64(const float* d_log_w, int64_t n, uint32_t u0, int64_t* d_anc,
+                                void* d_workspace, void* stream);
+/* Gather rows of a Point by ancestor index: dst[k] = src[anc[k]]. */
+int fab_gather_rows_f32(const float* d_src, float* d_dst, const int64_t* d_anc, int64_t n,
+                        int32_t row_floats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAB_B200_H */

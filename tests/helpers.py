@@ -1,0 +1,48 @@
+"""Shared builders for the parity tests: matched (oracle fp64, oracle fp32, product CUDA) objects."""
+import copy
+
+import torch
+
+import fab_torch_b200 as fb
+from oracle.realnvp import OracleRealNVP, randomize_last_layers
+from oracle.targets import OracleManyWell, OracleGMM, to_double
+
+
+def make_flows(dim, n_layers, nodes_per_dim, seed=0, last_std=0.05, perturb_base=True, device="cuda"):
+    """Returns (oracle fp64, oracle fp32, product on `device`) sharing the same fp32 weights."""
+    torch.manual_seed(seed)
+    fo = OracleRealNVP(dim, n_layers, nodes_per_dim)
+    if n_layers:
+        randomize_last_layers(fo, last_std, seed=seed + 1)
+    if perturb_base:
+        g = torch.Generator().manual_seed(seed + 2)
+        with torch.no_grad():
+            fo._nf_model.q0.loc.add_(torch.randn(1, dim, generator=g) * 0.2)
+            fo._nf_model.q0.log_scale.add_(torch.randn(1, dim, generator=g) * 0.1)
+    fo64 = copy.deepcopy(fo).double()
+    fp = fb.B200RealNVP(dim, n_layers, nodes_per_dim)
+    fp.load_state_dict(fo.state_dict())
+    if device is not None:
+        fp = fp.to(device)
+    return fo64, fo, fp
+
+
+def make_manywell(dim, device="cuda"):
+    return OracleManyWell(dim), fb.ManyWellEnergy(dim, use_gpu=(device == "cuda"))
+
+
+def make_gmm(dim, n_mixes, loc_scaling, log_var_scaling=0.1, seed=0, device="cuda"):
+    torch.manual_seed(seed)
+    to = OracleGMM(dim, n_mixes, loc_scaling, log_var_scaling)
+    torch.manual_seed(seed)
+    tp = fb.GMM(dim, n_mixes, loc_scaling, log_var_scaling, use_gpu=(device == "cuda"))
+    assert torch.equal(to.locs, tp.locs.cpu())
+    to64 = to_double(copy.deepcopy(to))
+    return to64, to, tp
+
+
+def rel_err(a, b):
+    """max |a-b| / max(1, |b|) elementwise -> scalar (a: test value, b: truth)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs() / b.abs().clamp_min(1.0)).max().item()

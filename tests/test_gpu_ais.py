@@ -1,0 +1,133 @@
+"""Whole-chain `sample_and_log_weights` on the GPU vs. the fp64 oracle with injected noise."""
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import fab_torch_b200 as fb
+from helpers import make_flows, make_manywell, make_gmm, rel_err
+from oracle.noise import Float32RecordingNoise
+from oracle.sampler import OracleAIS, OracleHMC, OracleMetropolis
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, alpha=2.0, **opkw):
+    fo64, fo, fp = make_flows(dim, K, npd, last_std=0.05)
+    if tk == "mw":
+        to, tp = make_manywell(dim)
+    else:
+        to, _, tp = make_gmm(dim, 4, 8.0)
+    if op_kind == "hmc":
+        op_o = OracleHMC(M, dim, fo64.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw).double()
+        op_p = fb.HamiltonianMonteCarlo(M, dim, fp.log_prob, tp.log_prob, alpha=alpha, p_target=p_target, **opkw).cuda()
+    else:
+        op_o = OracleMetropolis(M, dim, fo64.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw).double()
+        op_p = fb.Metropolis(M, dim, fp.log_prob, tp.log_prob, alpha=alpha, p_target=p_target, **opkw).cuda()
+    noise = Float32RecordingNoise()
+    op_o.noise = noise
+    ais_o = OracleAIS(fo64, to.log_prob, op_o, p_target=p_target, alpha=alpha,
+                      n_intermediate_distributions=M, distribution_spacing_type=spacing)
+    torch.manual_seed(21)
+    fo64._eps_override = noise.base_eps(B, dim, torch.float64, "cpu")
+    pt_o, lw_o = ais_o.sample_and_log_weights(B)
+    ais_p = fb.AnnealedImportanceSampler(fp, tp.log_prob, op_p, p_target=p_target, alpha=alpha,
+                                         n_intermediate_distributions=M,
+                                         distribution_spacing_type=spacing)
+    op_p.noise = fb.InjectedNoise(noise.record)
+    pt_p, lw_p = ais_p.sample_and_log_weights(B)
+    return (pt_o, lw_o, ais_o, op_o), (pt_p, lw_p, ais_p, op_p)
+
+
+AIS_CASES = [
+    dict(dim=32, K=10, npd=10, tk="mw", M=4, B=96, op_kind="hmc", epsilon=0.05, L=3),
+    dict(dim=32, K=10, npd=10, tk="mw", M=3, B=200, op_kind="hmc", epsilon=1.0, L=5),     # reference init step: mostly rejects / overflow
+    dict(dim=2, K=4, npd=40, tk="gmm", M=8, B=512, op_kind="metropolis", n_updates=1,
+         max_step_size=5.0, min_step_size=5.0, adjust_step_size=False),                     # config 1
+    dict(dim=2, K=0, npd=1, tk="gmm", M=12, B=300, op_kind="hmc", spacing="geometric",
+         p_target=True, alpha=None, epsilon=0.5, L=4, n_outer=2),
+]
+
+
+@pytest.mark.parametrize("case", AIS_CASES)
+def test_chain_parity(case):
+    (pt_o, lw_o, ais_o, op_o), (pt_p, lw_p, ais_p, op_p) = _run_pair(**case)
+    assert lw_p.shape == lw_o.shape and pt_p.x.shape == pt_o.x.shape
+    B = lw_o.shape[0]
+    dx = (pt_p.x.cpu().double() - pt_o.x).abs().max(dim=1).values
+    diverged = dx > 1e-2 * (1 + pt_o.x.abs().max(dim=1).values)
+    frac = diverged.float().mean().item()
+    assert frac <= 0.02, f"{frac:.3f} of the chains took a different accept branch"
+    ok = ~diverged
+    err_w = rel_err(lw_p.cpu()[ok], lw_o[ok])
+    assert err_w < 1e-4, f"log_w rel err {err_w:.3e}"
+    info_o, info_p = ais_o.get_logging_info(), ais_p.get_logging_info()
+    assert set(info_o) == set(info_p)
+    assert abs(info_p["ess_base"] - info_o["ess_base"]) < 1e-4 * max(info_o["ess_base"], 1e-3) + 1e-7
+    if frac == 0:
+        assert abs(info_p["log_Z"] - info_o["log_Z"]) < 1e-3
+        assert abs(info_p["ess_ais"] - info_o["ess_ais"]) < 1e-3 * max(info_o["ess_ais"], 1e-3) + 1e-7
+
+
+def test_log_z_of_normalised_gaussians():
+    """fab/sampling_methods/ais_test.py:21-64 made into an assertion: q=N(+.5,I), p=N(-.5,I),
+    alpha=1, fixed Metropolis step 2.0 -> log Z = 0; the error shrinks with more distributions."""
+    dim, B = 1, 10000
+    dim = 2   # kernels need d >= 2; the analytic answer is unchanged
+    errs = {}
+    for M in (1, 8, 32):
+        flow = fb.B200RealNVP(dim, 0, 1)
+        with torch.no_grad():
+            flow._nf_model.q0.loc.fill_(0.5)
+        flow = flow.cuda()
+        target = fb.DiagGaussianTarget(torch.zeros(dim) - 0.5, 1.0)
+        op = fb.Metropolis(M, dim, flow.log_prob, target.log_prob, n_updates=1, alpha=1.0,
+                           p_target=False, max_step_size=2.0, min_step_size=2.0,
+                           adjust_step_size=False).cuda()
+        ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=False, alpha=1.0,
+                                           n_intermediate_distributions=M)
+        torch.manual_seed(0)
+        pts, log_w = ais.sample_and_log_weights(B)
+        log_Z = torch.logsumexp(log_w, 0) - math.log(B)
+        errs[M] = abs(log_Z.item())
+        assert abs(ais.get_logging_info()["log_Z"] - log_Z.item()) < 1e-4
+    assert errs[32] < 0.05 and errs[8] < 0.1 and errs[1] < 0.3, errs
+
+
+def test_nan_filter_shrinks_batch():
+    """ais.py:190-213: particles with non-finite log_p/log_q are dropped (stable order) and log Z
+    still divides by the requested batch size (quirk 6)."""
+    fo64, fo, fp = make_flows(2, 0, 1, perturb_base=False)
+    with torch.no_grad():
+        fp._nf_model.q0.log_scale.fill_(math.log(60.0))      # base much wider than the target mask
+    to64, to, tp = make_gmm(2, 4, 8.0)
+    op = fb.Metropolis(3, 2, fp.log_prob, tp.log_prob, n_updates=1, alpha=2.0, p_target=False).cuda()
+    ais = fb.AnnealedImportanceSampler(fp, tp.log_prob, op, p_target=False, alpha=2.0,
+                                       n_intermediate_distributions=3)
+    B = 400
+    torch.manual_seed(3)
+    eps = torch.randn(B, 2)
+    fp._eps_override = eps.cuda()
+    pt, lw = ais.sample_and_log_weights(B)
+    x0 = (eps * 60.0).double()
+    keep = torch.isfinite(to64.log_prob(x0))
+    assert 0 < keep.sum() < B
+    assert lw.shape[0] == int(keep.sum()) == pt.x.shape[0]
+    assert torch.isfinite(pt.log_p).all() and torch.isfinite(pt.log_q).all()
+    info = ais.get_logging_info()
+    lz = torch.logsumexp(lw, 0).item() - math.log(B)
+    assert abs(info["log_Z"] - lz) < 1e-4
+
+
+def test_all_invalid_raises():
+    _, _, fp = make_flows(2, 0, 1, perturb_base=False)
+    with torch.no_grad():
+        fp._nf_model.q0.loc.fill_(1.0e4)
+    _, _, tp = make_gmm(2, 4, 8.0)
+    op = fb.Metropolis(2, 2, fp.log_prob, tp.log_prob, n_updates=1, alpha=2.0).cuda()
+    ais = fb.AnnealedImportanceSampler(fp, tp.log_prob, op, p_target=False, alpha=2.0,
+                                       n_intermediate_distributions=2)
+    with pytest.raises(Exception, match="No valid points generated in sampling the chain init"):
+        ais.sample_and_log_weights(64)

@@ -1,0 +1,50 @@
+import pytest
+import torch
+
+from helpers import make_manywell, make_gmm, rel_err
+import fab_torch_b200 as fb
+from oracle.targets import OracleDiagGaussian
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dim", [2, 32, 128])
+def test_manywell(dim):
+    to, tp = make_manywell(dim)
+    x = torch.randn(257, dim) * 1.7
+    x64 = x.double().requires_grad_(True)
+    ref = to.log_prob(x64)
+    gref = torch.autograd.grad(ref.sum(), x64)[0]
+    xg = x.cuda().requires_grad_(True)
+    lp = tp.log_prob(xg)
+    g = torch.autograd.grad(lp.sum(), xg)[0]
+    assert rel_err(lp, ref) < 1e-5
+    assert rel_err(g, gref) < 1e-5
+    assert abs(float(fb.ManyWellEnergy(32).log_Z) - 164.69567532) < 1e-6
+
+
+@pytest.mark.parametrize("dim,n_mixes,loc", [(2, 40, 40.0), (2, 4, 8.0), (3, 33, 5.0)])
+def test_gmm(dim, n_mixes, loc):
+    to64, _, tp = make_gmm(dim, n_mixes, loc, 1.0)
+    x = (torch.rand(300, dim) - 0.5) * 2.2 * loc
+    x64 = x.double().requires_grad_(True)
+    ref = to64.log_prob(x64)
+    gref = torch.autograd.grad(ref.sum(), x64)[0]
+    xg = x.cuda().requires_grad_(True)
+    lp = tp.log_prob(xg)
+    g = torch.autograd.grad(lp.sum(), xg)[0]
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(lp).cpu(), fin)
+    assert rel_err(lp.cpu()[fin], ref[fin]) < 1e-5
+    assert rel_err(g.cpu()[fin], gref[fin]) < 1e-4
+
+
+def test_gmm_mask_and_gaussian_target():
+    _, _, tp = make_gmm(2, 4, 8.0)
+    far = torch.full((3, 2), 1.0e3).cuda()
+    assert torch.isinf(tp.log_prob(far)).all()          # gmm.py:63-65
+    loc = torch.tensor([-0.5, -0.5, -0.5])
+    tgt = fb.DiagGaussianTarget(loc, 1.0)
+    ref = OracleDiagGaussian(loc.double(), 1.0)
+    x = torch.randn(100, 3)
+    assert rel_err(tgt.log_prob(x.cuda()), ref.log_prob(x.double())) < 1e-5
