@@ -33,6 +33,17 @@ def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, 
     torch.manual_seed(21)
     fo64._eps_override = noise.base_eps(B, dim, torch.float64, "cpu")
     pt_o, lw_o = ais_o.sample_and_log_weights(B)
+    # yardstick: the reference algorithm itself in fp32 on the CPU, same noise
+    if op_kind == "hmc":
+        op_32 = OracleHMC(M, dim, fo.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw)
+    else:
+        op_32 = OracleMetropolis(M, dim, fo.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw)
+    from oracle.noise import ReplayNoise
+    op_32.noise = ReplayNoise(copy.deepcopy(noise.record))
+    ais_32 = OracleAIS(fo, to.log_prob, op_32, p_target=p_target, alpha=alpha,
+                       n_intermediate_distributions=M, distribution_spacing_type=spacing)
+    fo._eps_override = noise.record["base_eps"][0]
+    _run_pair.cpu32 = ais_32.sample_and_log_weights(B)
     ais_p = fb.AnnealedImportanceSampler(fp, tp.log_prob, op_p, p_target=p_target, alpha=alpha,
                                          n_intermediate_distributions=M,
                                          distribution_spacing_type=spacing)
@@ -62,7 +73,15 @@ def test_chain_parity(case):
     assert frac <= 0.02, f"{frac:.3f} of the chains took a different accept branch"
     ok = ~diverged
     err_w = rel_err(lw_p.cpu()[ok], lw_o[ok])
-    assert err_w < 1e-4, f"log_w rel err {err_w:.3e}"
+    # the same algorithm in fp32 on the CPU (the reference's own arithmetic) sets the scale of
+    # what rounding alone does to this chain; the CUDA path must not be worse than ~that.
+    pt_32, lw_32 = _run_pair.cpu32
+    dx32 = (pt_32.x.double() - pt_o.x).abs().max(dim=1).values
+    ok32 = ~(dx32 > 1e-2 * (1 + pt_o.x.abs().max(dim=1).values))
+    err_32 = rel_err(lw_32[ok32], lw_o[ok32])
+    print(f"log_w rel err vs fp64 truth: cuda {err_w:.3e}, cpu-fp32 reference {err_32:.3e}; "
+          f"diverged chains: cuda {int(diverged.sum())}, cpu-fp32 {int((~ok32).sum())} of {B}")
+    assert err_w < max(1e-5, 4 * err_32), f"log_w rel err {err_w:.3e} (cpu fp32: {err_32:.3e})"
     info_o, info_p = ais_o.get_logging_info(), ais_p.get_logging_info()
     assert set(info_o) == set(info_p)
     assert abs(info_p["ess_base"] - info_o["ess_base"]) < 1e-4 * max(info_o["ess_base"], 1e-3) + 1e-7

@@ -106,9 +106,11 @@ def test_metropolis_transition(dim, K, npd, tk, M, i, n_updates, step, B, tune):
     x = fo.sample((B,)).detach()
     kw = dict(n_updates=n_updates, alpha=2.0, p_target=False, max_step_size=step,
               min_step_size=step * 0.2, adjust_step_size=tune)
-    op_o = OracleMetropolis(M, dim, fo64.log_prob, to.log_prob, **kw).double()
+    # fp32 oracle on purpose: `exp(gamma' - gamma)` overflows to inf (-> 0 -> reject,
+    # metropolis.py:63-64) at 88.7 in fp32 but not in fp64, so fp64 is a different algorithm here.
+    op_o = OracleMetropolis(M, dim, fo.log_prob, to.log_prob, **kw)
     op_o.noise = Float32RecordingNoise()
-    pt_o = _quantize(make_point(x.double(), fo64.log_prob, to.log_prob, with_grad=False))
+    pt_o = make_point(x, fo.log_prob, to.log_prob, with_grad=False)
     pt_p = _to_cuda_point(pt_o)
     out_o = op_o.transition(pt_o, i, beta)
     op_p = fb.Metropolis(M, dim, fp.log_prob, tp.log_prob, **kw).cuda()
