@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the AIS hot path: BASELINE.json metric "AIS particles/sec (Many-Well-32, 16 dists,
+HMC L=5)".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A *step* is one `AnnealedImportanceSampler.sample_and_log_weights(batch)` call (ais.py:53-87) on
+BASELINE config 2: Many-Well d=32, RealNVP 10 layers x width 320, 16 intermediate distributions,
+HMC L=5 / n_outer=1 (tuner on), 2048 particles per GPU (weak scaling: N GPUs carry 2048*N
+particles sharded over ranks; the only exchanges are the scalar ESS all-gather and the tuner's
+all-reduce).  Prints ONE JSON line on rank 0 (contract in the task statement); see DESIGN.md §6.
+
+`--impl reference` times the CPU port of the reference path (oracle/, pinned bit-for-bit against
+the reference in the build container; the reference itself is Python and cannot travel) on the
+host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(dim=32, n_layers=10, nodes_per_dim=10, M=16, L=5, n_outer=1, epsilon=1.0,
+           batch_per_gpu=2048, alpha=2.0, p_target=False)
+METRIC = "ais_particles_per_sec"
+UNIT = "particles/s"
+WORKLOAD = "manywell32_realnvp10x320_M16_hmcL5_b2048_per_gpu"
+
+
+def flops_per_particle_flow_pass(dim, K, W):
+    d1 = int(dim / 2 + 0.5)
+    d2 = dim - d1
+    return 2 * K * (d1 * W + W * W + 2 * W * d2 + dim * dim)        # F_f
+
+
+def algorithmic_flops_per_particle(cfg):
+    Ff = flops_per_particle_flow_pass(cfg["dim"], cfg["n_layers"], cfg["dim"] * cfg["nodes_per_dim"])
+    return Ff * (1 + 2 * (1 + cfg["M"] * cfg["L"] * cfg["n_outer"]))   # 163 * F_f at config 2
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p["bf16_tflops_sustained"],
+                    sm_max_mhz=p.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                sm_max_mhz=1965.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def build_cpu_port(cfg, batch):
+    """The reference path on the CPU: oracle port of AIS + HMC + Many-Well with the restated flow,
+    same architecture/initialisation as the GPU arm."""
+    from oracle.realnvp import OracleRealNVP, randomize_last_layers
+    from oracle.sampler import OracleAIS, OracleHMC
+    from oracle.targets import OracleManyWell
+    torch.manual_seed(0)
+    flow = OracleRealNVP(cfg["dim"], cfg["n_layers"], cfg["nodes_per_dim"])
+    randomize_last_layers(flow, 0.01, seed=1)
+    target = OracleManyWell(cfg["dim"])
+    op = OracleHMC(cfg["M"], cfg["dim"], flow.log_prob, target.log_prob, alpha=cfg["alpha"],
+                   p_target=cfg["p_target"], epsilon=cfg["epsilon"], n_outer=cfg["n_outer"],
+                   L=cfg["L"])
+    ais = OracleAIS(flow, target.log_prob, op, p_target=cfg["p_target"], alpha=cfg["alpha"],
+                    n_intermediate_distributions=cfg["M"])
+    return ais
+
+
+def time_cpu_port(cfg, batch, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    ais = build_cpu_port(cfg, batch)
+    torch.manual_seed(1234)
+    for _ in range(warmup):
+        ais.sample_and_log_weights(batch)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ais.sample_and_log_weights(batch)
+        ts.append(time.perf_counter() - t0)
+    return ts, ais.get_logging_info()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = CFG["batch_per_gpu"]
+    ts, info = time_cpu_port(CFG, batch, args.steps, args.warmup)
+    total = float(np.sum(ts))
+    value = batch * len(ts) / total
+    cores = torch.get_num_threads()
+    sample = (f"each step = one full sample_and_log_weights({batch}) call of the workload "
+              f"(fp32, torch CPU, {cores} threads); particles/s is per-particle so the same figure "
+              f"holds for the {args.gpus}-GPU global batch")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total / len(ts), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=WORKLOAD, global_batch=batch * args.gpus, **{
+                    k: CFG[k] for k in ("dim", "n_layers", "M", "L", "n_outer")}),
+                impl="reference",
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, log_Z=info["log_Z"])
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                   "sw_power_cap"), r[4:8]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)),
+                    power_w_max=float(np.max(pw)), samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def build_gpu(cfg, device, group):
+    import fab_torch_b200 as fb
+    torch.manual_seed(0)                     # identical weights on every rank
+    flow = fb.B200RealNVP(cfg["dim"], cfg["n_layers"], cfg["nodes_per_dim"])
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():                    # non-zero last layers, N(0, 0.01^2)
+        for k in range(cfg["n_layers"]):
+            lin = flow._nf_model.flows[2 * k].linears[2]
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.01)
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.01)
+    flow = flow.to(device)
+    target = fb.ManyWellEnergy(cfg["dim"])
+    op = fb.HamiltonianMonteCarlo(cfg["M"], cfg["dim"], flow.log_prob, target.log_prob,
+                                  alpha=cfg["alpha"], p_target=cfg["p_target"],
+                                  epsilon=cfg["epsilon"], n_outer=cfg["n_outer"], L=cfg["L"]).to(device)
+    ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=cfg["p_target"],
+                                       alpha=cfg["alpha"], n_intermediate_distributions=cfg["M"],
+                                       process_group=group)
+    return flow, target, op, ais
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    import fab_torch_b200 as fb
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    cfg = CFG
+    B_local = cfg["batch_per_gpu"]
+    B_global = B_local * world
+    flow, target, op, ais = build_gpu(cfg, device, group)
+    torch.manual_seed(1234 + rank)           # independent particles per rank
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident metric -------------------------------------------------------------
+    for _ in range(args.warmup):
+        ais.sample_and_log_weights(B_global)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.fill_(1.0)                     # evict L2 between timed iterations (untimed)
+        s.record()
+        ais.sample_and_log_weights(B_global)
+        e.record()
+    barrier()
+    ms = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device=device)
+    info = ais.get_logging_info()
+    # ---- end-to-end: host noise -> H2D -> chain -> D2H of the result ------------------------
+    M, d, no = cfg["M"], cfg["dim"], cfg["n_outer"]
+    h_eps = torch.randn(B_local, d).pin_memory()
+    h_mom = torch.randn(M, no, B_local, d).pin_memory()
+    h_exp = torch.empty(M, no, B_local).exponential_(1.0).pin_memory()
+    h_x = torch.empty(B_local, d).pin_memory()
+    h_w = torch.empty(B_local).pin_memory()
+    h2d = (h_eps.numel() + h_mom.numel() + h_exp.numel()) * 4
+    d2h = (h_x.numel() + h_w.numel()) * 4 + 40
+
+    def e2e_step():
+        d_eps = h_eps.to(device, non_blocking=True)
+        d_mom = h_mom.to(device, non_blocking=True)
+        d_exp = h_exp.to(device, non_blocking=True)
+        flow._eps_override = d_eps
+        op.chain_noise_override = [(d_mom[j], d_exp[j]) for j in range(M)]
+        pt, lw = ais.sample_and_log_weights(B_global)
+        n = lw.shape[0]
+        h_x[:n].copy_(pt.x, non_blocking=True)
+        h_w[:n].copy_(lw, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(h_w[:n].max())
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    for s, e in ev2:
+        flush.fill_(1.0)
+        s.record()
+        e2e_step()
+        e.record()
+    barrier()
+    ms_e2e = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2)], dtype=torch.float64,
+                          device=device)
+    clock_rec = clocks.stop() if rank == 0 else None
+    # ---- roofline of the dominant kernel (k_hmc_step), timed per launch on its stream ---------
+    op.chain_noise_override = None
+    k_ms = ais.time_transitions(B_global, repeats=2)
+    k_ms_t = torch.tensor([k_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(k_ms_t, op=dist.ReduceOp.MAX)
+    total_ms, total_e2e_ms, kernel_ms = float(ms), float(ms_e2e), float(k_ms_t)
+    if rank == 0:
+        peaks = measured_peaks()
+        value = B_global * args.steps / (total_ms * 1e-3)
+        e2e_value = B_global * args.steps / (total_e2e_ms * 1e-3)
+        Ff = flops_per_particle_flow_pass(d, cfg["n_layers"], d * cfg["nodes_per_dim"])
+        flops_per_launch = 2.0 * Ff * cfg["L"] * B_local          # value+grad per leapfrog
+        achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+        sm_mhz = (clock_rec or {}).get("sm_max_mhz") or peaks["sm_max_mhz"]
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+        ffma_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roof = dict(bound="tensor", achieved=achieved, peak=peaks["bf16_tflops_sustained"],
+                    unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"], traffic=None,
+                    kernel="k_hmc_step", kernel_ms=kernel_ms, peak_source=peaks["source"] +
+                    " bf16_tflops_sustained (kernel timed inside a long step)",
+                    pipe="fp32_ffma", pipe_peak=ffma_peak, pipe_frac=achieved / ffma_peak,
+                    flops_per_launch=flops_per_launch,
+                    note="fp32 parity bar (1e-5 rel) => GEMMs run on the FP32 FFMA pipe; frac vs the "
+                         "tensor peak is reported as required, pipe_frac vs the FFMA ceiling "
+                         "n_sm*128*2*sm_max_mhz is the bound that applies (DESIGN.md §4)")
+        launches_per_step = 1 + 3 + 2 + cfg["M"] * cfg["n_outer"] * (2 if world > 1 else 1) + 3 + 2
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=WORKLOAD, global_batch=B_global, l2_flush_between_steps=True,
+                                tuner="on", **{k: cfg[k] for k in ("dim", "n_layers", "M", "L", "n_outer")}),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d * world,
+                             d2h_bytes_per_step=d2h * world, ms_per_step=total_e2e_ms / args.steps),
+                    gpu_launches=launches_per_step * args.steps, clocks=clock_rec, roofline=roof,
+                    log_Z=info["log_Z"], ess_ais=info["ess_ais"])
+        if world == 1 and not args.no_cpu_baseline:
+            ts, cinfo = time_cpu_port(cfg, B_local, steps=2, warmup=1)
+            cv = B_local * len(ts) / float(np.sum(ts))
+            line["cpu_baseline"] = dict(
+                value=cv, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"2 timed + 1 warm-up full sample_and_log_weights({B_local}) calls, fp32, "
+                       f"{float(np.sum(ts)):.1f} s of CPU work", log_Z=cinfo["log_Z"])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,7 +127,7 @@ class AnnealedImportanceSampler:
         return (make_gamma(self.B_space[j], self.alpha, self.p_target),
                 make_gamma(self.B_space[j + 1], self.alpha, self.p_target))
 
-    def _run_chain(self, batch_size: int, logging: bool):
+    def _run_chain(self, batch_size: int, logging: bool, timings=None):
         """Enqueue the whole chain; returns device tensors + the device record (no sync)."""
         flow, op, target = self.base_distribution, self.transition_operator, self._target
         dev = flow._device()
@@ -158,12 +158,35 @@ class AnnealedImportanceSampler:
         if logging:
             self._ess(pt.log_p, pt.log_q, counts[0:1], rec[0:3])   # ESS over base weights
         M = self.n_intermediate_distributions
+        chain_noise = op.chain_noise(M, n, d, dev)
         for j in range(1, M + 1):
-            op.run(pt, j, self.B_space[j], log_w, self._w_update(j), n_active=counts[0:1])
+            if timings is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            op.run(pt, j, self.B_space[j], log_w, self._w_update(j), n_active=counts[0:1],
+                   noise=chain_noise[j - 1])
+            if timings is not None:
+                e1.record()
+                timings.append((e0, e1))
         self._filter(pt, log_w, counts[0:1], counts[1:2])          # "chain end"
         if logging:
             self._ess(log_w, None, counts[1:2], rec[3:6])
         return pt, log_w, counts, rec
+
+    def time_transitions(self, batch_size: int, repeats: int = 1) -> float:
+        """Mean device time (ms) of one fused transition launch, measured with CUDA events on the
+        launching stream around every transition of `repeats` chains (bench.py roofline)."""
+        world, rank = self._world()
+        local = batch_size // world
+        self.transition_operator.process_group = self.process_group
+        total, count = 0.0, 0
+        for _ in range(repeats):
+            timings = []
+            self._run_chain(local, False, timings=timings)
+            torch.cuda.current_stream().synchronize()
+            total += sum(a.elapsed_time(b) for a, b in timings)
+            count += len(timings)
+        return total / max(count, 1)
 
     def sample_and_log_weights(self, batch_size: int, logging: bool = True
                                ) -> Tuple[Point, torch.Tensor]:

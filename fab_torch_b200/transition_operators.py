@@ -117,6 +117,7 @@ class TransitionOperator(nn.Module):
         object.__setattr__(self, "_flow", flow)
         object.__setattr__(self, "_target", target)
         self.noise = DeviceNoise()
+        self.chain_noise_override = None  # one-shot pre-drawn noise for the next chain (e.g. from host)
         self.process_group = None       # set by the sampler for particle-parallel runs
         self.register_buffer("_stats", torch.zeros(2 * _lib.FAB_MAX_UPDATES), persistent=False)
         self._ws = None
@@ -265,11 +266,24 @@ class HamiltonianMonteCarlo(TransitionOperator):
             self._prop_bufs = (mk(), mk())
         return self._prop_bufs[slot]
 
+    def chain_noise(self, M: int, n: int, d: int, dev):
+        """Noise for a whole chain, one (momentum[n_outer,n,d], exponential[n_outer,n]) pair per
+        transition.  With the default device RNG everything is drawn in two launches."""
+        if self.chain_noise_override is not None:
+            pre, self.chain_noise_override = self.chain_noise_override, None
+            return pre
+        if type(self.noise) is DeviceNoise:
+            mom = torch.randn((M, self.n_outer, n, d), dtype=torch.float32, device=dev)
+            exp = torch.empty((M, self.n_outer, n), dtype=torch.float32, device=dev).exponential_(1.0)
+            return [(mom[j], exp[j]) for j in range(M)]
+        return [(self.noise.momentum(j + 1, self.n_outer, n, d, dev),
+                 self.noise.exponential(j + 1, self.n_outer, n, dev)) for j in range(M)]
+
     def run(self, point: Point, i: int, beta, log_w: Optional[torch.Tensor] = None,
-            w_update=None, n_active: Optional[torch.Tensor] = None) -> Point:
+            w_update=None, n_active: Optional[torch.Tensor] = None, noise=None) -> Point:
         """One HMC transition at distribution i.  `w_update=(g_w, g_next)` (the sampler's gammas at
         beta_i and beta_{i+1}) fuses the AIS log-weight update log_w += g_next(x) - g_w(x)
-        (ais.py:93-100) into the last outer step."""
+        (ais.py:93-100) into the last outer step.  `noise` = pre-drawn (momentum, exponential)."""
         self._check_point(point, need_grad=True)
         flow, target = self._flow, self._target
         dev = point.x.device
@@ -278,8 +292,11 @@ class HamiltonianMonteCarlo(TransitionOperator):
         g = make_gamma(beta, self.alpha, self.p_target)
         fuse_w = w_update is not None and log_w is not None
         g_w, g_next = w_update if fuse_w else (g, g)
-        mom = self.noise.momentum(i, self.n_outer, n, d, dev)
-        exp = self.noise.exponential(i, self.n_outer, n, dev)
+        if noise is not None:
+            mom, exp = noise
+        else:
+            mom = self.noise.momentum(i, self.n_outer, n, d, dev)
+            exp = self.noise.exponential(i, self.n_outer, n, dev)
         ws = self._workspace(int(L.fab_hmc_workspace_bytes(flow.desc(), n)), dev)
         world = self._world()
         st = self._state()
@@ -348,8 +365,20 @@ class Metropolis(TransitionOperator):
         s = self.noise_scalings.detach().cpu()
         return {"noise_scaling_0_0": s[0, 0].item(), "noise_scaling_0_-1": s[0, -1].item()}
 
+    def chain_noise(self, M: int, n: int, d: int, dev):
+        """One (proposal[n_updates,n,d], uniform[n_updates,n]) pair per transition."""
+        if self.chain_noise_override is not None:
+            pre, self.chain_noise_override = self.chain_noise_override, None
+            return pre
+        if type(self.noise) is DeviceNoise:
+            prop = torch.randn((M, self.n_updates, n, d), dtype=torch.float32, device=dev)
+            unif = torch.rand((M, self.n_updates, n), dtype=torch.float32, device=dev)
+            return [(prop[j], unif[j]) for j in range(M)]
+        return [(self.noise.proposal(j + 1, self.n_updates, n, d, dev),
+                 self.noise.uniform(j + 1, self.n_updates, n, dev)) for j in range(M)]
+
     def run(self, point: Point, i: int, beta, log_w: Optional[torch.Tensor] = None,
-            w_update=None, n_active: Optional[torch.Tensor] = None) -> Point:
+            w_update=None, n_active: Optional[torch.Tensor] = None, noise=None) -> Point:
         self._check_point(point, need_grad=False)
         flow, target = self._flow, self._target
         dev = point.x.device
@@ -358,8 +387,11 @@ class Metropolis(TransitionOperator):
         g = make_gamma(beta, self.alpha, self.p_target)
         fuse_w = w_update is not None and log_w is not None
         g_w, g_next = w_update if fuse_w else (g, g)
-        prop = self.noise.proposal(i, self.n_updates, n, d, dev)
-        unif = self.noise.uniform(i, self.n_updates, n, dev)
+        if noise is not None:
+            prop, unif = noise
+        else:
+            prop = self.noise.proposal(i, self.n_updates, n, d, dev)
+            unif = self.noise.uniform(i, self.n_updates, n, dev)
         ws = self._workspace(int(L.fab_metropolis_workspace_bytes(flow.desc(), n, self.n_updates)),
                              dev)
         world = self._world()

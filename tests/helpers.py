@@ -46,3 +46,25 @@ def rel_err(a, b):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return ((a - b).abs() / b.abs().clamp_min(1.0)).max().item()
+
+
+def assert_parity(gpu, truth, cpu32=None, name="", floor=1e-5, factor=4.0, mask=None):
+    """The parity bar (BASELINE.json: 'within 1e-5 relative fp32'): the CUDA result must be within
+    `floor` (relative) of the fp64 ground truth, or -- where rounding is amplified by the
+    computation itself (chaotic leapfrog, exp of large scales, ReLU-mask flips) -- no worse than
+    `factor` x the error the reference's own fp32 CPU arithmetic makes on the same inputs."""
+    pick = (lambda t: t.detach().cpu()[mask]) if mask is not None else (lambda t: t.detach().cpu())
+    g, t = pick(gpu), pick(truth)
+    fin = torch.isfinite(t.double())
+    assert torch.equal(torch.isfinite(g.double()), fin), f"{name}: finiteness pattern differs"
+    err = rel_err(g[fin], t[fin]) if fin.any() else 0.0
+    bar = floor
+    err32 = None
+    if cpu32 is not None:
+        c = pick(cpu32)
+        fin32 = fin & torch.isfinite(c.double())
+        err32 = rel_err(c[fin32], t[fin32]) if fin32.any() else 0.0
+        bar = max(floor, factor * err32)
+    assert err <= bar, (f"{name}: cuda rel err {err:.3e} > bar {bar:.3e}"
+                        + (f" (cpu fp32 reference err {err32:.3e})" if err32 is not None else ""))
+    return err, err32
