@@ -10,25 +10,36 @@
 #include <stdint.h>
 #include "fab_b200.h"
 
+#ifndef FAB_NT
 #define FAB_NT 320              // threads per tile CTA (10 warps)
+#endif
 #define FAB_NWARPS (FAB_NT / 32)
+#ifndef FAB_TN
+#define FAB_TN 4                // output columns per GEMM unit (tile_gemm.cuh)
+#endif
 #define FAB_FULL 0xffffffffu
 
 __host__ __device__ __forceinline__ int fab_round4(int v) { return (v + 3) & ~3; }
 
 // Shared-memory carve-up of one tile CTA; all offsets in floats.  Filled on the host, passed by
-// value to the kernels (so host and device agree by construction).
+// value to the kernels (so host and device agree by construction).  zs, vs, z1b, par, h1, h2 are
+// GEMM operands in the k4-major layout of tile_gemm.cuh (float4 [K4][T]); zs, z1b, h1, h2 carry
+// extra k4 blocks at the end (the constant-one bias block; for h1 also the [gv] block of the
+// merged backward GEMM).  Everything else is row-major per particle.
 struct TileLayout {
     int T;              // particles per CTA
     int d, DP;          // dim and round_up(dim,4)
     int d1, d2, D1P, P2;// conditioner width, transformed width, pads (P2 = round_up(2*d2,4))
-    int WP, WW;         // padded hidden width, mask words per row = ceil(WP/32)
+    int WP;             // padded hidden width
+    int MW;             // ReLU-mask words per layer and MLP stage
     int K;              // coupling layers
     int red_floats;     // capacity of the split-K reduction buffer
     // offsets
     int o_zs, o_vs, o_z1b, o_par, o_h1, o_h2, o_red;
-    int o_sy2, o_ses, o_m1, o_m2;       // saved-for-backward, [K][T][...]
+    int o_sy2, o_ses, o_m1, o_m2;       // saved-for-backward, [K][...]
     int o_ld;                           // [T] running log-det
+    int o_scl;                          // [T][d2] coupling scales of the current layer
+    int o_const;                        // loc[DP], log_scale[DP], 1/scale[DP], logs[K]
     int o_state;                        // kernel-specific state area
     int total_floats;
 };
@@ -41,25 +52,38 @@ __host__ inline TileLayout make_tile_layout(const fab_flow_desc& f, int T, bool 
     L.d1 = f.d1; L.d2 = f.d2; L.D1P = fab_round4(f.d1 > 0 ? f.d1 : 1);
     L.P2 = fab_round4(2 * f.d2 > 0 ? 2 * f.d2 : 1);
     L.WP = f.width_pad > 0 ? f.width_pad : 4;
-    L.WW = (L.WP + 31) / 32;
+    L.MW = 4 * ((T * L.WP / 4 + 31) / 32);
     L.K = f.n_layers;
-    int maxN = L.WP > L.DP ? L.WP : L.DP;
-    L.red_floats = 2 * T * maxN;
+    // reduction buffer: large enough for the k-splits that let each wide GEMM (N >= WP) occupy all
+    // FAB_NT threads (same arithmetic as gemm_plan in tile_gemm.cuh); rows are padded by 4 floats.
+    auto need = [&](int NP, int K4) {
+        int ks = FAB_NT / (NP / FAB_TN > 0 ? NP / FAB_TN : 1);
+        if (ks < 1) ks = 1;
+        if (ks > K4) ks = K4;
+        if (ks > 8) ks = 8;
+        return ks * T * (NP + 4);
+    };
+    L.red_floats = need(L.DP + L.WP, L.DP / 4 + 1);
+    if (need(L.WP, L.WP / 4 + 1) > L.red_floats) L.red_floats = need(L.WP, L.WP / 4 + 1);
+    if (need(L.WP, L.P2 / 4) > L.red_floats) L.red_floats = need(L.WP, L.P2 / 4);
+    if (need(L.DP, (L.WP + L.DP) / 4) > L.red_floats) L.red_floats = need(L.DP, (L.WP + L.DP) / 4);
     int o = 0;
     auto take = [&](int n) { int r = o; o += fab_round4(n); return r; };
-    L.o_zs = take(T * L.DP);
+    L.o_zs = take(T * (L.DP + 4));
     L.o_vs = take(T * L.DP);
-    L.o_z1b = take(T * L.D1P);
+    L.o_z1b = take(T * (L.D1P + 4));
     L.o_par = take(T * L.P2);
-    L.o_h1 = take(T * L.WP);
-    L.o_h2 = take(T * L.WP);
+    L.o_h1 = take(T * (L.WP + (L.DP > 4 ? L.DP : 4)));
+    L.o_h2 = take(T * (L.WP + 4));
     L.o_red = take(L.red_floats);
     int KS = with_grad ? L.K : 0;
     L.o_sy2 = take(KS * T * L.d2);
     L.o_ses = take(KS * T * L.d2);
-    L.o_m1 = take(KS * T * L.WW);
-    L.o_m2 = take(KS * T * L.WW);
+    L.o_m1 = take(KS * L.MW);
+    L.o_m2 = take(KS * L.MW);
     L.o_ld = take(T);
+    L.o_scl = take(T * L.d2);
+    L.o_const = take(3 * L.DP + L.K);
     L.o_state = take(state_floats);
     L.total_floats = o;
     return L;

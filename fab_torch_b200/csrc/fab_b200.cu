@@ -101,18 +101,14 @@ int64_t fab_flow_desc_init(fab_flow_desc* d, int32_t dim, int32_t width, int32_t
     d->off_layers = o;
     int64_t l = 0;
     auto packed = [](int64_t K, int64_t NP) { return ((K + 3) / 4) * NP * 4; };
-    d->o_mix = l;     l += packed(dim, DP);
-    d->o_mix_t = l;   l += packed(dim, DP);
-    d->o_mix_inv = l; l += packed(dim, DP);
-    d->o_w1 = l;      l += packed(d->d1, WP);
-    d->o_w2 = l;      l += packed(WP, WP);
-    d->o_w3 = l;      l += packed(WP, P2);
-    d->o_w3t = l;     l += packed(2 * d->d2, WP);
+    d->o_mw1 = l;     l += packed(DP + 4, DP + WP);
+    d->o_w2 = l;      l += packed(WP + 4, WP);
+    d->o_w3 = l;      l += packed(WP + 4, P2);
+    d->o_w3t = l;     l += packed(P2, WP);
     d->o_w2t = l;     l += packed(WP, WP);
-    d->o_w1t = l;     l += packed(WP, D1P);
-    d->o_b1 = l;      l += WP;
-    d->o_b2 = l;      l += WP;
-    d->o_b3 = l;      l += P2;
+    d->o_w1mt = l;    l += packed(WP + DP, DP);
+    d->o_w1 = l;      l += packed(D1P + 4, WP);
+    d->o_mix_inv = l; l += packed(DP, DP);
     d->o_logs = l;    l += 4;
     d->layer_stride = l;
     d->total_floats = o + (int64_t)n_layers * l;

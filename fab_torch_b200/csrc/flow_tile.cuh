@@ -10,11 +10,18 @@
 //                       u' = [v1,y2] @ Wmix^-1;  log q -= sum(scale) - sum(log_S)
 //   inverse,  layer k:  v = u @ Wmix; (shift,scale) = MLP(v1);  y2 = (v2-shift)*exp(-scale);
 //                       u' = [v1,y2];           log q += sum(log_S) - sum(scale)
+// Per layer and direction this is three GEMMs (include/fab_b200.h: o_mw1/o_w2/o_w3 and
+// o_w3t/o_w2t/o_w1mt): the mixing matrix is merged into the neighbouring MLP GEMM and biases ride
+// along as an extra K row against a constant-one activation block.
+//
+// zs, vs, z1b, par, h1, h2 are GEMM operands in the k4-major layout (tile_gemm.cuh): element
+// (p, n) of any of them sits at float index kidx<T>(p, n), independent of the buffer width.
 #pragma once
 #include "tile_gemm.cuh"
 
 struct TileBufs {
-    float *zs, *vs, *z1b, *par, *h1, *h2, *red, *sy2, *ses, *ld;
+    float *zs, *vs, *z1b, *par, *h1, *h2, *red, *sy2, *ses, *ld, *scl;
+    float *loc, *lsc, *inv, *logs;          // staged constants
     uint32_t *m1, *m2;
 };
 
@@ -23,83 +30,117 @@ __device__ __forceinline__ TileBufs tile_bufs(const TileLayout& L, float* smem) 
     b.zs = smem + L.o_zs;   b.vs = smem + L.o_vs;   b.z1b = smem + L.o_z1b;
     b.par = smem + L.o_par; b.h1 = smem + L.o_h1;   b.h2 = smem + L.o_h2;
     b.red = smem + L.o_red; b.sy2 = smem + L.o_sy2; b.ses = smem + L.o_ses;
-    b.ld = smem + L.o_ld;
+    b.ld = smem + L.o_ld;   b.scl = smem + L.o_scl;
+    b.loc = smem + L.o_const; b.lsc = b.loc + L.DP; b.inv = b.lsc + L.DP; b.logs = b.inv + L.DP;
     b.m1 = reinterpret_cast<uint32_t*>(smem + L.o_m1);
     b.m2 = reinterpret_cast<uint32_t*>(smem + L.o_m2);
     return b;
 }
 
-// Zero the padding-sensitive buffers once per kernel (pads must stay exactly 0 because the packed
-// operands multiply them by 0 and 0*inf would poison a row).
-__device__ __forceinline__ void tile_zero_pads(const TileLayout& L, const TileBufs& b) {
-    for (int i = threadIdx.x; i < L.T * L.DP; i += FAB_NT) { b.zs[i] = 0.f; b.vs[i] = 0.f; }
-    for (int i = threadIdx.x; i < L.T * L.D1P; i += FAB_NT) b.z1b[i] = 0.f;
-    for (int i = threadIdx.x; i < L.T * L.P2; i += FAB_NT) b.par[i] = 0.f;
-    for (int i = threadIdx.x; i < L.T * L.WP; i += FAB_NT) { b.h1[i] = 0.f; b.h2[i] = 0.f; }
+template <int T>
+__device__ __forceinline__ void set_one_block(float* buf, int k4_block) {
+    // the constant (1,0,0,0) activation block that multiplies the bias row of an operand
+    for (int p = threadIdx.x; p < T; p += FAB_NT)
+        reinterpret_cast<float4*>(buf)[(size_t)k4_block * T + p] = make_float4(1.f, 0.f, 0.f, 0.f);
 }
 
-// hidden-layer epilogue: h = relu(sum + bias) (FWD) or h = mask ? sum : 0 (BWD), one 32-column
-// word of one particle per warp iteration so the ReLU mask is a single ballot.
+// Once per kernel: zero the operand buffers (pad rows/columns must stay exactly 0 because the
+// packed weights multiply them by 0 and 0*inf would poison a row), set the bias blocks, and stage
+// the small per-flow constants (base loc / log_scale, per-layer sum(log_S)) in shared memory so
+// that no serial code path waits on an L2 round trip.
+template <int T>
+__device__ __forceinline__ void tile_init(const TileLayout& L, const TileBufs& b,
+                                          const fab_flow_desc& f, const float* __restrict__ blob) {
+    for (int i = threadIdx.x; i < T * (L.DP + 4); i += FAB_NT) b.zs[i] = 0.f;
+    for (int i = threadIdx.x; i < T * L.DP; i += FAB_NT) b.vs[i] = 0.f;
+    for (int i = threadIdx.x; i < T * (L.D1P + 4); i += FAB_NT) b.z1b[i] = 0.f;
+    for (int i = threadIdx.x; i < T * L.P2; i += FAB_NT) b.par[i] = 0.f;
+    for (int i = threadIdx.x; i < T * (L.WP + (L.DP > 4 ? L.DP : 4)); i += FAB_NT) b.h1[i] = 0.f;
+    for (int i = threadIdx.x; i < T * (L.WP + 4); i += FAB_NT) b.h2[i] = 0.f;
+    for (int j = threadIdx.x; j < L.DP; j += FAB_NT) {
+        const float loc = j < L.d ? __ldg(blob + f.off_base_loc + j) : 0.f;
+        const float ls = j < L.d ? __ldg(blob + f.off_base_log_scale + j) : 0.f;
+        b.loc[j] = loc; b.lsc[j] = ls; b.inv[j] = expf(-ls);
+    }
+    for (int k = threadIdx.x; k < L.K; k += FAB_NT)
+        b.logs[k] = __ldg(blob + f.off_layers + (size_t)k * f.layer_stride + f.o_logs);
+    __syncthreads();
+    set_one_block<T>(b.zs, L.DP / 4);
+    set_one_block<T>(b.z1b, L.D1P / 4);
+    set_one_block<T>(b.h1, L.WP / 4);
+    set_one_block<T>(b.h2, L.WP / 4);
+    __syncthreads();
+}
+
+// hidden-layer epilogue, one float4 (4 consecutive columns of one particle) per lane and step:
+// FWD: h = relu(sum)  (bias already inside the GEMM), ReLU masks = 4 ballots per 32 float4;
+// BWD: h = mask ? sum : 0.   `col0` = first column of this block inside the GEMM output.
 template <int T, bool FWD, bool SAVE>
 __device__ __forceinline__ void hidden_epilogue(const TileLayout& L, const float* red, int KS,
-                                                const float* __restrict__ bias, float* h,
-                                                uint32_t* mask) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int w = warp; w < T * L.WW; w += FAB_NWARPS) {
-        const int p = w / L.WW;
-        const int n = (w - p * L.WW) * 32 + lane;
-        const bool in = n < L.WP;
-        float v = 0.f;
-        if (in) v = red_sum<T>(red, KS, L.WP, p, n);
+                                                int NP, int col0, float* h, uint32_t* mask) {
+    const int lane = threadIdx.x & 31;
+    const int nq = T * (L.WP >> 2);
+    float4* h4 = reinterpret_cast<float4*>(h);
+    for (int q0 = (threadIdx.x & ~31); q0 < nq; q0 += FAB_NT) {
+        const int q = q0 + lane;
+        const bool in = q < nq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) {
+            const int k4 = q / T;
+            const int p = q - k4 * T;
+            v = red_sum4<T>(red, KS, NP, p, col0 + (k4 << 2));
+        }
+        uint32_t* mw = mask + ((q0 >> 5) << 2);
         if (FWD) {
-            if (in) v += __ldg(bias + n);
-            const bool pos = in && (v > 0.f);
+            const bool px = in && v.x > 0.f, py = in && v.y > 0.f, pz = in && v.z > 0.f,
+                       pw = in && v.w > 0.f;
             if (SAVE) {
-                const uint32_t bits = __ballot_sync(FAB_FULL, pos);
-                if (lane == 0) mask[w] = bits;
+                const uint32_t bx = __ballot_sync(FAB_FULL, px), by = __ballot_sync(FAB_FULL, py),
+                               bz = __ballot_sync(FAB_FULL, pz), bw = __ballot_sync(FAB_FULL, pw);
+                if (lane == 0) *reinterpret_cast<uint4*>(mw) = make_uint4(bx, by, bz, bw);
             }
-            if (in) h[p * L.WP + n] = pos ? v : 0.f;
+            if (in) h4[q] = make_float4(px ? v.x : 0.f, py ? v.y : 0.f, pz ? v.z : 0.f, pw ? v.w : 0.f);
         } else {
-            const uint32_t bits = mask[w];
-            if (in) h[p * L.WP + n] = ((bits >> lane) & 1u) ? v : 0.f;
+            const uint4 bits = *reinterpret_cast<const uint4*>(mw);
+            if (in)
+                h4[q] = make_float4((bits.x >> lane) & 1u ? v.x : 0.f, (bits.y >> lane) & 1u ? v.y : 0.f,
+                                    (bits.z >> lane) & 1u ? v.z : 0.f, (bits.w >> lane) & 1u ? v.w : 0.f);
         }
     }
 }
 
-// The conditioner MLP on z1b -> red holds the (shift|scale) partial sums (NP = P2).
+// MLP stages 2 and 3 (h1 -> h2 -> [shift|scale] partial sums in red, NP = P2); returns KS.
+// `next_*` describe the GEMM that follows the coupling step (prefetched behind the last barrier).
 template <int T, bool SAVE>
-__device__ __forceinline__ GemmSplit conditioner_forward(const TileLayout& L, const TileBufs& b,
-                                                         const float* __restrict__ lay,
-                                                         const fab_flow_desc& f, int k) {
-    GemmSplit g = tile_gemm<T>(b.z1b, L.D1P, L.D1P / 4,
-                               reinterpret_cast<const float4*>(lay + f.o_w1), L.WP, b.red,
-                               L.red_floats);
+__device__ __forceinline__ int mlp_tail(const TileLayout& L, const TileBufs& b,
+                                        const float* __restrict__ lay, const fab_flow_desc& f,
+                                        int k, const float* next_wp, int next_K4, int next_NP) {
+    int KS = tile_gemm<T>(b.h1, L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
+                          b.red, L.red_floats);
+    tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w3), L.P2,
+                          L.red_floats);
     __syncthreads();
-    hidden_epilogue<T, true, SAVE>(L, b.red, g.KS, lay + f.o_b1, b.h1,
-                                   SAVE ? b.m1 + (size_t)k * T * L.WW : nullptr);
+    hidden_epilogue<T, true, SAVE>(L, b.red, KS, L.WP, 0, b.h2,
+                                   SAVE ? b.m2 + (size_t)k * L.MW : nullptr);
     __syncthreads();
-    g = tile_gemm<T>(b.h1, L.WP, L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
-                     b.red, L.red_floats);
+    KS = tile_gemm<T>(b.h2, L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w3), L.P2,
+                      b.red, L.red_floats);
+    if (next_wp)
+        tile_gemm_prefetch<T>(next_K4, reinterpret_cast<const float4*>(next_wp), next_NP,
+                              L.red_floats);
     __syncthreads();
-    hidden_epilogue<T, true, SAVE>(L, b.red, g.KS, lay + f.o_b2, b.h2,
-                                   SAVE ? b.m2 + (size_t)k * T * L.WW : nullptr);
-    __syncthreads();
-    g = tile_gemm<T>(b.h2, L.WP, L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w3), L.P2,
-                     b.red, L.red_floats);
-    __syncthreads();
-    return g;
+    return KS;
 }
 
-// per-particle  ld[p] += add - sum_j par[p][d2 + j]   (par holds [shift | scale] after coupling)
+// per-particle  ld[p] += add - sum_j scl[p][j]
 template <int T>
-__device__ __forceinline__ void logdet_accumulate(const TileLayout& L, const TileBufs& b,
-                                                  float add, float sign) {
+__device__ __forceinline__ void logdet_accumulate(const TileLayout& L, const TileBufs& b, float add) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int p = warp; p < T; p += FAB_NWARPS) {
         float s = 0.f;
-        for (int j = lane; j < L.d2; j += 32) s += b.par[p * L.P2 + L.d2 + j];
+        for (int j = lane; j < L.d2; j += 32) s += b.scl[p * L.d2 + j];
         s = warp_sum(s);
-        if (lane == 0) b.ld[p] += add + sign * s;
+        if (lane == 0) b.ld[p] += add - s;
     }
 }
 
@@ -110,57 +151,61 @@ template <int T, bool SAVE>
 __device__ void flow_inverse(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                              const float* __restrict__ blob, float* lq_out) {
     for (int p = threadIdx.x; p < T; p += FAB_NT) b.ld[p] = 0.f;
-    __syncthreads();
+    const int NP1 = L.DP + L.WP;
     for (int k = L.K - 1; k >= 0; --k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
-        // v = z @ Wmix
-        GemmSplit g = tile_gemm<T>(b.zs, L.DP, L.DP / 4,
-                                   reinterpret_cast<const float4*>(lay + f.o_mix), L.DP, b.red,
-                                   L.red_floats);
+        // [v | h1pre] = [z | 1] @ [Wmix | Wmix[:, :d1] W1^T ; 0 | b1]
+        int KS = tile_gemm<T>(b.zs, L.DP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_mw1),
+                              NP1, b.red, L.red_floats);
+        tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
+                              L.red_floats);
         __syncthreads();
-        for (int i = threadIdx.x; i < T * L.DP; i += FAB_NT) {
-            const int p = i / L.DP, n = i - p * L.DP;
+        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+            int p, n;
+            kdecode<T>(e, p, n);
             if (n < L.d) {
-                const float v = red_sum<T>(b.red, g.KS, L.DP, p, n);
-                b.vs[i] = v;
-                if (n < L.d1) { b.z1b[p * L.D1P + n] = v; b.zs[i] = v; }
+                const float v = red_sum<T>(b.red, KS, NP1, p, n);
+                b.vs[e] = v;
+                if (n < L.d1) b.zs[e] = v;
             }
         }
+        hidden_epilogue<T, true, SAVE>(L, b.red, KS, NP1, L.DP, b.h1,
+                                       SAVE ? b.m1 + (size_t)k * L.MW : nullptr);
+        if (SAVE) set_one_block<T>(b.h1, L.WP / 4);   // flow_backward parks [gv] in these blocks
         __syncthreads();
-        g = conditioner_forward<T, SAVE>(L, b, lay, f, k);
+        KS = mlp_tail<T, SAVE>(L, b, lay, f, k, k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr,
+                               L.DP / 4 + 1, NP1);
         // coupling inverse: y2 = (v2 - shift) * exp(-scale)
         for (int i = threadIdx.x; i < T * L.d2; i += FAB_NT) {
-            const int p = i / L.d2, j = i - p * L.d2;
-            const float shift = red_sum<T>(b.red, g.KS, L.P2, p, j) + __ldg(lay + f.o_b3 + j);
-            const float scale = red_sum<T>(b.red, g.KS, L.P2, p, L.d2 + j) +
-                                __ldg(lay + f.o_b3 + L.d2 + j);
+            const int j = i / T, p = i - j * T;
+            const float shift = red_sum<T>(b.red, KS, L.P2, p, j);
+            const float scale = red_sum<T>(b.red, KS, L.P2, p, L.d2 + j);
             const float es = expf(-scale);
-            const float y2 = (b.vs[p * L.DP + L.d1 + j] - shift) * es;
-            b.zs[p * L.DP + L.d1 + j] = y2;
-            b.par[p * L.P2 + L.d2 + j] = scale;
+            const int e = kidx<T>(p, L.d1 + j);
+            const float y2 = (b.vs[e] - shift) * es;
+            b.zs[e] = y2;
+            b.scl[p * L.d2 + j] = scale;
             if (SAVE) {
                 b.sy2[((size_t)k * T + p) * L.d2 + j] = y2;
                 b.ses[((size_t)k * T + p) * L.d2 + j] = es;
             }
         }
         __syncthreads();
-        logdet_accumulate<T>(L, b, __ldg(lay + f.o_logs), -1.f);
-        // (the next phase that touches par/ld is at least one barrier away)
+        logdet_accumulate<T>(L, b, b.logs[k]);
+        // (scl / ld are next touched after at least one more barrier)
     }
     __syncthreads();
     // base Gaussian: log N(z; loc, exp(log_scale)) and its z-gradient
     {
-        const float* loc = blob + f.off_base_loc;
-        const float* lsc = blob + f.off_base_log_scale;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int p = warp; p < T; p += FAB_NWARPS) {
             float s = 0.f;
             for (int j = lane; j < L.d; j += 32) {
-                const float ls = __ldg(lsc + j);
-                const float inv = expf(-ls);
-                const float u = (b.zs[p * L.DP + j] - __ldg(loc + j)) * inv;
-                s += ls + 0.5f * u * u;
-                if (SAVE) b.vs[p * L.DP + j] = -u * inv;
+                const float inv = b.inv[j];
+                const int e = kidx<T>(p, j);
+                const float u = (b.zs[e] - b.loc[j]) * inv;
+                s += b.lsc[j] + 0.5f * u * u;
+                if (SAVE) b.vs[e] = -u * inv;
             }
             s = warp_sum(s);
             if (lane == 0)
@@ -175,56 +220,59 @@ template <int T>
 __device__ void flow_backward(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                               const float* __restrict__ blob) {
     float* gs = b.vs;
+    float* gv = b.h1 + (size_t)(L.WP / 4) * T * 4;     // [gv] blocks behind gh1 (k4-major)
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
-        // coupling backward (see SURVEY Appendix B): gv2 = g2*es, gshift = -gv2, gscale = -g2*y2 - 1
+        // coupling backward (SURVEY Appendix B): gv2 = g2*es, gshift = -gv2, gscale = -g2*y2 - 1
         for (int i = threadIdx.x; i < T * L.d2; i += FAB_NT) {
-            const int p = i / L.d2, j = i - p * L.d2;
+            const int j = i / T, p = i - j * T;
             const float es = b.ses[((size_t)k * T + p) * L.d2 + j];
             const float y2 = b.sy2[((size_t)k * T + p) * L.d2 + j];
-            const float g2 = gs[p * L.DP + L.d1 + j];
+            const int e = kidx<T>(p, L.d1 + j);
+            const float g2 = gs[e];
             const float gv2 = g2 * es;
-            b.par[p * L.P2 + j] = -gv2;
-            b.par[p * L.P2 + L.d2 + j] = -g2 * y2 - 1.0f;
-            gs[p * L.DP + L.d1 + j] = gv2;
+            b.par[kidx<T>(p, j)] = -gv2;
+            b.par[kidx<T>(p, L.d2 + j)] = -g2 * y2 - 1.0f;
+            gv[e] = gv2;
+        }
+        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+            int p, n;
+            kdecode<T>(e, p, n);
+            if (n < L.d1) gv[e] = gs[e];
+            else if (n >= L.d) gv[e] = 0.f;
         }
         __syncthreads();
         // gh2 = (gparam @ W3) * m2
-        GemmSplit g = tile_gemm<T>(b.par, L.P2, L.P2 / 4,
-                                   reinterpret_cast<const float4*>(lay + f.o_w3t), L.WP, b.red,
-                                   L.red_floats);
+        int KS = tile_gemm<T>(b.par, L.P2 / 4, reinterpret_cast<const float4*>(lay + f.o_w3t), L.WP,
+                              b.red, L.red_floats);
+        tile_gemm_prefetch<T>(L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w2t), L.WP,
+                              L.red_floats);
         __syncthreads();
-        hidden_epilogue<T, false, false>(L, b.red, g.KS, nullptr, b.h2,
-                                         b.m2 + (size_t)k * T * L.WW);
+        hidden_epilogue<T, false, false>(L, b.red, KS, L.WP, 0, b.h2, b.m2 + (size_t)k * L.MW);
         __syncthreads();
         // gh1 = (gh2 @ W2) * m1
-        g = tile_gemm<T>(b.h2, L.WP, L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w2t),
-                         L.WP, b.red, L.red_floats);
+        KS = tile_gemm<T>(b.h2, L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w2t), L.WP,
+                          b.red, L.red_floats);
+        tile_gemm_prefetch<T>((L.WP + L.DP) / 4, reinterpret_cast<const float4*>(lay + f.o_w1mt),
+                              L.DP, L.red_floats);
         __syncthreads();
-        hidden_epilogue<T, false, false>(L, b.red, g.KS, nullptr, b.h1,
-                                         b.m1 + (size_t)k * T * L.WW);
+        hidden_epilogue<T, false, false>(L, b.red, KS, L.WP, 0, b.h1, b.m1 + (size_t)k * L.MW);
         __syncthreads();
-        // gv1 = g1 + gh1 @ W1
-        g = tile_gemm<T>(b.h1, L.WP, L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w1t),
-                         L.D1P, b.red, L.red_floats);
+        // g_u = [gh1 | gv] @ [W1 Wmix[:, :d1]^T ; Wmix^T]
+        KS = tile_gemm<T>(b.h1, (L.WP + L.DP) / 4, reinterpret_cast<const float4*>(lay + f.o_w1mt),
+                          L.DP, b.red, L.red_floats);
+        if (k + 1 < L.K)
+            tile_gemm_prefetch<T>(L.P2 / 4,
+                                  reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t),
+                                  L.WP, L.red_floats);
         __syncthreads();
-        for (int i = threadIdx.x; i < T * L.d1; i += FAB_NT) {
-            const int p = i / L.d1, n = i - p * L.d1;
-            gs[p * L.DP + n] += red_sum<T>(b.red, g.KS, L.D1P, p, n);
-        }
-        __syncthreads();
-        // g_u = gv @ Wmix^T
-        g = tile_gemm<T>(gs, L.DP, L.DP / 4, reinterpret_cast<const float4*>(lay + f.o_mix_t),
-                         L.DP, b.red, L.red_floats);
-        __syncthreads();
-        for (int i = threadIdx.x; i < T * L.DP; i += FAB_NT) {
-            const int p = i / L.DP, n = i - p * L.DP;
-            if (n < L.d) gs[i] = red_sum<T>(b.red, g.KS, L.DP, p, n);
+        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+            int p, n;
+            kdecode<T>(e, p, n);
+            if (n < L.d) gs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
         }
         __syncthreads();
     }
-    // par is used as a zero-padded GEMM operand only inside this function and as scratch in
-    // flow_inverse/flow_sample (columns < 2*d2), so its pad columns are still 0.
 }
 
 // eps in b.zs -> x in b.zs, forward-pass log q in lq_out[p].
@@ -232,48 +280,61 @@ template <int T>
 __device__ void flow_sample(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                             const float* __restrict__ blob, float* lq_out) {
     {   // base: z = loc + exp(log_scale)*eps ; log p0 = -d/2 log 2pi - sum(log_scale + eps^2/2)
-        const float* loc = blob + f.off_base_loc;
-        const float* lsc = blob + f.off_base_log_scale;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int p = warp; p < T; p += FAB_NWARPS) {
             float s = 0.f;
             for (int j = lane; j < L.d; j += 32) {
-                const float ls = __ldg(lsc + j);
-                const float e = b.zs[p * L.DP + j];
-                s += ls + 0.5f * e * e;
-                b.zs[p * L.DP + j] = __ldg(loc + j) + expf(ls) * e;
+                const float ls = b.lsc[j];
+                const int e = kidx<T>(p, j);
+                const float ev = b.zs[e];
+                s += ls + 0.5f * ev * ev;
+                b.zs[e] = b.loc[j] + expf(ls) * ev;
             }
             s = warp_sum(s);
             if (lane == 0) b.ld[p] = -0.5f * (float)L.d * 1.8378770664093453f - s;
         }
     }
+    set_one_block<T>(b.h1, L.WP / 4);
     __syncthreads();
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
-        for (int i = threadIdx.x; i < T * L.d1; i += FAB_NT) {
-            const int p = i / L.d1, n = i - p * L.d1;
-            b.z1b[p * L.D1P + n] = b.zs[p * L.DP + n];
+        for (int e = threadIdx.x; e < T * L.D1P; e += FAB_NT) {
+            int p, n;
+            kdecode<T>(e, p, n);
+            if (n < L.d1) b.z1b[e] = b.zs[e];
         }
         __syncthreads();
-        GemmSplit g = conditioner_forward<T, false>(L, b, lay, f, k);
+        int KS = tile_gemm<T>(b.z1b, L.D1P / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w1),
+                              L.WP, b.red, L.red_floats);
+        tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
+                              L.red_floats);
+        __syncthreads();
+        hidden_epilogue<T, true, false>(L, b.red, KS, L.WP, 0, b.h1, nullptr);
+        __syncthreads();
+        KS = mlp_tail<T, false>(L, b, lay, f, k, lay + f.o_mix_inv, L.DP / 4, L.DP);
         for (int i = threadIdx.x; i < T * L.d2; i += FAB_NT) {
-            const int p = i / L.d2, j = i - p * L.d2;
-            const float shift = red_sum<T>(b.red, g.KS, L.P2, p, j) + __ldg(lay + f.o_b3 + j);
-            const float scale = red_sum<T>(b.red, g.KS, L.P2, p, L.d2 + j) +
-                                __ldg(lay + f.o_b3 + L.d2 + j);
-            b.zs[p * L.DP + L.d1 + j] = b.zs[p * L.DP + L.d1 + j] * expf(scale) + shift;
-            b.par[p * L.P2 + L.d2 + j] = scale;
+            const int j = i / T, p = i - j * T;
+            const float shift = red_sum<T>(b.red, KS, L.P2, p, j);
+            const float scale = red_sum<T>(b.red, KS, L.P2, p, L.d2 + j);
+            const int e = kidx<T>(p, L.d1 + j);
+            b.zs[e] = b.zs[e] * expf(scale) + shift;
+            b.scl[p * L.d2 + j] = scale;
         }
         __syncthreads();
         // log q -= sum(scale);  log q -= (-sum log_S)
-        logdet_accumulate<T>(L, b, __ldg(lay + f.o_logs), -1.f);
+        logdet_accumulate<T>(L, b, b.logs[k]);
         // u' = [v1,y2] @ Wmix^-1
-        g = tile_gemm<T>(b.zs, L.DP, L.DP / 4, reinterpret_cast<const float4*>(lay + f.o_mix_inv),
-                         L.DP, b.red, L.red_floats);
+        KS = tile_gemm<T>(b.zs, L.DP / 4, reinterpret_cast<const float4*>(lay + f.o_mix_inv), L.DP,
+                          b.red, L.red_floats);
+        if (k + 1 < L.K)
+            tile_gemm_prefetch<T>(L.D1P / 4 + 1,
+                                  reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w1),
+                                  L.WP, L.red_floats);
         __syncthreads();
-        for (int i = threadIdx.x; i < T * L.DP; i += FAB_NT) {
-            const int p = i / L.DP, n = i - p * L.DP;
-            if (n < L.d) b.zs[i] = red_sum<T>(b.red, g.KS, L.DP, p, n);
+        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+            int p, n;
+            kdecode<T>(e, p, n);
+            if (n < L.d) b.zs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
         }
         __syncthreads();
     }

@@ -25,19 +25,52 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, int d, const
 __device__ __forceinline__ void copy_tile(float* dst, const float* src, int n) {
     for (int i = threadIdx.x; i < n; i += FAB_NT) dst[i] = src[i];
 }
+// k4-major operand buffer (tile_gemm.cuh) <-> global rows / row-major shared tiles
+template <int T>
+__device__ __forceinline__ void load_rows_k4(float* dst, const float* __restrict__ src, int d, int DP,
+                                             long long row0, int np) {
+    for (int e = threadIdx.x; e < T * DP; e += FAB_NT) {
+        int p, n;
+        kdecode<T>(e, p, n);
+        dst[e] = (p < np && n < d) ? __ldg(src + (row0 + p) * d + n) : 0.f;
+    }
+}
+template <int T>
+__device__ __forceinline__ void store_rows_k4(float* __restrict__ dst, int d, const float* src,
+                                              long long row0, int np) {
+    for (int i = threadIdx.x; i < np * d; i += FAB_NT) {
+        const int p = i / d, j = i - p * d;
+        dst[(row0 + p) * d + j] = src[kidx<T>(p, j)];
+    }
+}
+template <int T>
+__device__ __forceinline__ void rows_to_k4(float* dst_k4, const float* src_rows, int DP) {
+    for (int e = threadIdx.x; e < T * DP; e += FAB_NT) {
+        int p, n;
+        kdecode<T>(e, p, n);
+        dst_k4[e] = src_rows[p * DP + n];
+    }
+}
+template <int T>
+__device__ __forceinline__ void k4_to_rows(float* dst_rows, const float* src_k4, int DP) {
+    for (int i = threadIdx.x; i < T * DP; i += FAB_NT) {
+        const int p = i / DP, n = i - p * DP;
+        dst_rows[i] = src_k4[kidx<T>(p, n)];
+    }
+}
 
-// Evaluate log q (+grad), log p (+grad) at the rows x[T][DP] (shared).  Outputs in shared:
-// lq[T], lp[T], gq[T][DP], gp[T][DP] (the last two only when GRAD).
+// Evaluate log q (+grad), log p (+grad) at the rows x[T][DP] (shared, row-major, pads zero).
+// Outputs in shared: lq[T], lp[T], gq[T][DP], gp[T][DP] (the last two only when GRAD).
 template <int T, bool GRAD>
 __device__ void eval_point(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                            const float* __restrict__ blob, const fab_target_desc& tgt,
                            const float* x, float* lq, float* lp, float* gq, float* gp) {
-    copy_tile(b.zs, x, T * L.DP);
+    rows_to_k4<T>(b.zs, x, L.DP);
     __syncthreads();
     flow_inverse<T, GRAD>(L, b, f, blob, lq);
     if (GRAD) {
         flow_backward<T>(L, b, f, blob);
-        copy_tile(gq, b.vs, T * L.DP);
+        k4_to_rows<T>(gq, b.vs, L.DP);
     }
     target_tile<T>(tgt, x, L.DP, L.d, lp, GRAD ? gp : nullptr);
     __syncthreads();
@@ -56,12 +89,11 @@ k_flow_sample(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
     float* lq = smem + L.o_state;
     const long long row0 = (long long)blockIdx.x * T;
     const int np = (int)min((long long)T, n - row0);
-    tile_zero_pads(L, b);
-    __syncthreads();
-    load_rows(b.zs, L.DP, eps, L.d, row0, np, T);
+    tile_init<T>(L, b, f, blob);
+    load_rows_k4<T>(b.zs, eps, L.d, L.DP, row0, np);
     __syncthreads();
     flow_sample<T>(L, b, f, blob, lq);
-    store_rows(x, L.d, b.zs, L.DP, row0, np);
+    store_rows_k4<T>(x, L.d, b.zs, row0, np);
     for (int p = threadIdx.x; p < np; p += FAB_NT) log_q[row0 + p] = lq[p];
 }
 
@@ -75,14 +107,13 @@ k_flow_logprob(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
     float* lq = smem + L.o_state;
     const long long row0 = (long long)blockIdx.x * T;
     const int np = (int)min((long long)T, n - row0);
-    tile_zero_pads(L, b);
-    __syncthreads();
-    load_rows(b.zs, L.DP, x, L.d, row0, np, T);
+    tile_init<T>(L, b, f, blob);
+    load_rows_k4<T>(b.zs, x, L.d, L.DP, row0, np);
     __syncthreads();
     flow_inverse<T, GRAD>(L, b, f, blob, lq);
     if (GRAD) {
         flow_backward<T>(L, b, f, blob);
-        store_rows(grad, L.d, b.vs, L.DP, row0, np);
+        store_rows_k4<T>(grad, L.d, b.vs, row0, np);
     }
     for (int p = threadIdx.x; p < np; p += FAB_NT) log_q[row0 + p] = lq[p];
 }
@@ -108,12 +139,11 @@ k_ais_init(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
     float* slp = slq + fab_round4(T);
     const long long row0 = (long long)blockIdx.x * T;
     const int np = (int)min((long long)T, n - row0);
-    tile_zero_pads(L, b);
-    __syncthreads();
-    load_rows(b.zs, L.DP, eps, L.d, row0, np, T);
+    tile_init<T>(L, b, f, blob);
+    load_rows_k4<T>(b.zs, eps, L.d, L.DP, row0, np);
     __syncthreads();
     flow_sample<T>(L, b, f, blob, slq0);
-    copy_tile(sx, b.zs, T * L.DP);
+    k4_to_rows<T>(sx, b.zs, L.DP);
     __syncthreads();
     if (GRAD) {
         // create_point(with_grad=True) re-evaluates log q by the inverse pass
@@ -234,7 +264,7 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     if (np > 0) {
-        tile_zero_pads(L, b);
+        tile_init<T>(L, b, f, blob);
         load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
         load_rows(cgq, L.DP, cur.d_grad_log_q, L.d, row0, np, T);
         load_rows(cgp, L.DP, cur.d_grad_log_p, L.d, row0, np, T);
@@ -422,7 +452,7 @@ k_metropolis(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_
     if (np < 0) np = 0;
     for (int u = threadIdx.x; u < 4 * FAB_MAX_UPDATES; u += FAB_NT) blk[u] = 0.f;
     if (np > 0) {
-        tile_zero_pads(L, b);
+        tile_init<T>(L, b, f, blob);
         load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
         for (int p = threadIdx.x; p < T; p += FAB_NT) {
             const float lq = p < np ? cur.d_log_q[row0 + p] : 0.f;

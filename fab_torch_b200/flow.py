@@ -195,17 +195,34 @@ class B200RealNVP(TrainableDistribution):
         b3 = b3[:, perm]
         Wm, Wm_inv, logs = self._mixing()
         t = lambda M: M.transpose(1, 2)
+        dd, d1, W = d.dim, d.d1, d.width
+        z = lambda r, c: W1.new_zeros(K, r, c)
+        # merged operands (products in float64, rounded once)
+        mw1 = z(DP + 4, DP + WP)                       # o_mw1: [z | 1] -> [v | h1pre]
+        mw1[:, :dd, :dd] = Wm
+        mw1[:, :dd, DP:DP + W] = (Wm[:, :, :d1].double() @ t(W1).double()).float()
+        mw1[:, DP, DP:DP + W] = b1
+        w2 = z(WP + 4, WP)                             # o_w2: [h1 | 1] -> h2pre
+        w2[:, :W, :W] = t(W2)
+        w2[:, WP, :W] = b2
+        w3 = z(WP + 4, P2)                             # o_w3: [h2 | 1] -> (shift | scale)
+        w3[:, :W, :2 * d.d2] = t(W3)
+        w3[:, WP, :2 * d.d2] = b3
+        w1mt = z(WP + DP, DP)                          # o_w1mt: [gh1 | gv] -> g_u
+        w1mt[:, :W, :dd] = (W1.double() @ t(Wm[:, :, :d1]).double()).float()
+        w1mt[:, WP:WP + dd, :dd] = t(Wm)
+        w1 = z(D1P + 4, WP)                            # o_w1 (sampling): [z1 | 1] -> h1pre
+        w1[:, :d1, :W] = t(W1)
+        w1[:, D1P, :W] = b1
         parts = [
-            _pack_operand(Wm, DP, DP),                 # o_mix     M[k][n] = W[k][n]
-            _pack_operand(t(Wm), DP, DP),              # o_mix_t   M[k][n] = W[n][k]
-            _pack_operand(Wm_inv, DP, DP),             # o_mix_inv
-            _pack_operand(t(W1), D1P, WP),             # o_w1      M[k][n] = W1[n][k]
-            _pack_operand(t(W2), WP, WP),              # o_w2
-            _pack_operand(t(W3), WP, P2),              # o_w3
+            _pack_operand(mw1, DP + 4, DP + WP),
+            _pack_operand(w2, WP + 4, WP),
+            _pack_operand(w3, WP + 4, P2),
             _pack_operand(W3, P2, WP),                 # o_w3t     M[k][n] = W3p[k][n]
-            _pack_operand(W2, WP, WP),                 # o_w2t
-            _pack_operand(W1, WP, D1P),                # o_w1t
-            _pad_last(b1, WP), _pad_last(b2, WP), _pad_last(b3, P2),
+            _pack_operand(W2, WP, WP),                 # o_w2t     M[k][n] = W2[k][n]
+            _pack_operand(w1mt, WP + DP, DP),
+            _pack_operand(w1, D1P + 4, WP),
+            _pack_operand(Wm_inv, DP, DP),             # o_mix_inv
             _pad_last(logs[:, None], 4),
         ]
         layers = torch.cat(parts, dim=1)

@@ -48,21 +48,33 @@ extern "C" {
  * so that consecutive threads (consecutive n) read consecutive 16-byte words.
  * The hidden width is padded to WP = round_up(W, 4) with zero weights/biases.
  *
+ * Biases are folded into the GEMMs: an operand whose input is an activation buffer carries one
+ * extra k4 block whose first row is the bias (other three rows 0); the kernels keep a constant
+ * (1,0,0,0) block at the end of the corresponding activation buffer.  The d x d mixing matrix of
+ * each InvertibleAffine is merged into the neighbouring MLP GEMM (one GEMM + one barrier pair less
+ * per layer pass in both directions); the merged products are formed in float64 on the host.
+ *
  * Blob layout (float offsets):  [base block][layer 0 block][layer 1 block]...
  *   base block : loc[DP], log_scale[DP]                         DP = round_up(d,4)
  *   layer block (all offsets relative to the layer block start; layer k of the reference's
- *   flow list, k = 0 is applied first when sampling):
- *     o_mix     packed  M[k][n] = Wmix[k][n]        K=d  N=d    inverse direction  z @ W
- *     o_mix_t   packed  M[k][n] = Wmix[n][k]        K=d  N=d    gradient           g @ W^T
- *     o_mix_inv packed  M[k][n] = Wmix^-1[k][n]     K=d  N=d    sampling direction z @ W^-1
- *     o_w1      packed  M[k][n] = W1[n][k]          K=d1 N=WP   (nn.Linear weight is [out,in])
- *     o_w2      packed  M[k][n] = W2[n][k]          K=WP N=WP
- *     o_w3      packed  M[k][n] = W3[perm(n)][k]    K=WP N=2*d2  columns de-interleaved:
- *                                                   n <  d2 -> shift row 2n, n >= d2 -> scale row 2(n-d2)+1
- *     o_w3t     packed  M[k][n] = W3[perm(k)][n]    K=2*d2 N=WP
- *     o_w2t     packed  M[k][n] = W2[k][n]          K=WP N=WP
- *     o_w1t     packed  M[k][n] = W1[k][n]          K=WP N=d1
- *     o_b1[WP], o_b2[WP], o_b3[P2] (de-interleaved like o_w3; P2 = round_up(2*d2,4))
+ *   flow list, k = 0 is applied first when sampling).  W1 [W,d1], W2 [W,W], W3 [2*d2,W] are the
+ *   nn.Linear weights ([out,in]); W3p/b3p = W3/b3 with rows de-interleaved (first the d2 shift
+ *   rows 0,2,4.., then the d2 scale rows 1,3,5..); P2 = round_up(2*d2,4), D1P = round_up(d1,4).
+ *   inverse direction (log_prob):
+ *     o_mw1   K=DP+4  N=DP+WP  in = [z | 1]            out = [v = z@Wmix | h1pre]
+ *                              M[k<d][n<d] = Wmix[k][n];  M[k<d][DP+j] = (Wmix[:, :d1] @ W1^T)[k][j];
+ *                              M[DP][DP+j] = b1[j]
+ *     o_w2    K=WP+4  N=WP     in = [h1 | 1]           M[k][n] = W2[n][k];   M[WP][n] = b2[n]
+ *     o_w3    K=WP+4  N=P2     in = [h2 | 1]           M[k][n] = W3p[n][k];  M[WP][n] = b3p[n]
+ *   input-gradient sweep:
+ *     o_w3t   K=P2    N=WP     in = gparam             M[k][n] = W3p[k][n]
+ *     o_w2t   K=WP    N=WP     in = gh2                M[k][n] = W2[k][n]
+ *     o_w1mt  K=WP+DP N=DP     in = [gh1 | gv]         M[k<W][n] = (W1 @ Wmix[:, :d1]^T)[k][n];
+ *                                                      M[WP+i][n] = Wmix[n][i]      (g @ Wmix^T)
+ *   sampling direction:
+ *     o_w1    K=D1P+4 N=WP     in = [z1 | 1]           M[k][n] = W1[n][k];   M[D1P][n] = b1[n]
+ *     o_mix_inv K=DP  N=DP     in = [v1,y2]            M[k][n] = Wmix^-1[k][n]
+ *     (o_w2, o_w3 are shared with the inverse direction)
  *     o_logs[4] : [0] = sum(log_S) of this layer's InvertibleAffine
  * ------------------------------------------------------------------------------------- */
 typedef struct fab_flow_desc {
@@ -75,9 +87,9 @@ typedef struct fab_flow_desc {
     int64_t total_floats; /* blob size                           */
     int64_t off_base_loc, off_base_log_scale;
     int64_t off_layers, layer_stride;
-    int64_t o_mix, o_mix_t, o_mix_inv;
-    int64_t o_w1, o_w2, o_w3, o_w3t, o_w2t, o_w1t;
-    int64_t o_b1, o_b2, o_b3, o_logs;
+    int64_t o_mw1, o_w2, o_w3;
+    int64_t o_w3t, o_w2t, o_w1mt;
+    int64_t o_w1, o_mix_inv, o_logs;
 } fab_flow_desc;
 
 /* Fills every field of *desc from (dim, width, n_layers); returns total_floats or <0. */
