@@ -27,6 +27,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
            "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    extra = os.environ.get("FAB_NVCC_FLAGS", "").split()
+    if extra:                      # experiment knobs, e.g. -DFAB_NT=640 -DFAB_TN=2 -DFAB_PF=4
+        cmd[1:1] = extra
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     print("[fab_torch_b200] " + " ".join(cmd), flush=True)

@@ -11,7 +11,10 @@
 #include "fab_b200.h"
 
 #ifndef FAB_NT
-#define FAB_NT 320              // threads per tile CTA (10 warps)
+#define FAB_NT 256              // threads per tile CTA (8 warps = 2 per scheduler; best of the sweep in profiles/)
+#endif
+#ifndef FAB_MIN_CTAS
+#define FAB_MIN_CTAS 1          // co-resident tile CTAs per SM the kernels are compiled for
 #endif
 #define FAB_NWARPS (FAB_NT / 32)
 #ifndef FAB_TN
@@ -23,11 +26,11 @@ __host__ __device__ __forceinline__ int fab_round4(int v) { return (v + 3) & ~3;
 
 // Shared-memory carve-up of one tile CTA; all offsets in floats.  Filled on the host, passed by
 // value to the kernels (so host and device agree by construction).  zs, vs, z1b, par, h1, h2 are
-// GEMM operands in the k4-major layout of tile_gemm.cuh (float4 [K4][T]); zs, z1b, h1, h2 carry
-// extra k4 blocks at the end (the constant-one bias block; for h1 also the [gv] block of the
-// merged backward GEMM).  Everything else is row-major per particle.
+// GEMM operands in the k-major / particle-fastest layout of tile_gemm.cuh (act[k][TP], TP = T
+// rounded up to 4); zs, z1b, h1, h2 carry 4 extra rows at the end (the constant-one bias row; for
+// h1 also the [gv] rows of the merged backward GEMM).  Everything else is row-major per particle.
 struct TileLayout {
-    int T;              // particles per CTA
+    int T, TP;          // particles per CTA, rounded up to 4
     int d, DP;          // dim and round_up(dim,4)
     int d1, d2, D1P, P2;// conditioner width, transformed width, pads (P2 = round_up(2*d2,4))
     int WP;             // padded hidden width
@@ -48,11 +51,12 @@ struct TileLayout {
 __host__ inline TileLayout make_tile_layout(const fab_flow_desc& f, int T, bool with_grad,
                                             int state_floats) {
     TileLayout L{};
-    L.T = T; L.d = f.dim; L.DP = fab_round4(f.dim);
+    L.T = T; L.TP = fab_round4(T); L.d = f.dim; L.DP = fab_round4(f.dim);
+    const int TP = L.TP;
     L.d1 = f.d1; L.d2 = f.d2; L.D1P = fab_round4(f.d1 > 0 ? f.d1 : 1);
     L.P2 = fab_round4(2 * f.d2 > 0 ? 2 * f.d2 : 1);
     L.WP = f.width_pad > 0 ? f.width_pad : 4;
-    L.MW = 4 * ((T * L.WP / 4 + 31) / 32);
+    L.MW = 4 * ((TP * L.WP / 4 + 31) / 32);
     L.K = f.n_layers;
     // reduction buffer: large enough for the k-splits that let each wide GEMM (N >= WP) occupy all
     // FAB_NT threads (same arithmetic as gemm_plan in tile_gemm.cuh); rows are padded by 4 floats.
@@ -69,12 +73,12 @@ __host__ inline TileLayout make_tile_layout(const fab_flow_desc& f, int T, bool 
     if (need(L.DP, (L.WP + L.DP) / 4) > L.red_floats) L.red_floats = need(L.DP, (L.WP + L.DP) / 4);
     int o = 0;
     auto take = [&](int n) { int r = o; o += fab_round4(n); return r; };
-    L.o_zs = take(T * (L.DP + 4));
-    L.o_vs = take(T * L.DP);
-    L.o_z1b = take(T * (L.D1P + 4));
-    L.o_par = take(T * L.P2);
-    L.o_h1 = take(T * (L.WP + (L.DP > 4 ? L.DP : 4)));
-    L.o_h2 = take(T * (L.WP + 4));
+    L.o_zs = take(TP * (L.DP + 4));
+    L.o_vs = take(TP * L.DP);
+    L.o_z1b = take(TP * (L.D1P + 4));
+    L.o_par = take(TP * L.P2);
+    L.o_h1 = take(TP * (L.WP + (L.DP > 4 ? L.DP : 4)));
+    L.o_h2 = take(TP * (L.WP + 4));
     L.o_red = take(L.red_floats);
     int KS = with_grad ? L.K : 0;
     L.o_sy2 = take(KS * T * L.d2);

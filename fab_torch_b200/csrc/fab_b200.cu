@@ -1,6 +1,7 @@
 // libfab_b200.so -- C ABI (include/fab_b200.h) over the sm_100a kernels.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -44,14 +45,25 @@ template <typename StateFn>
 int pick_tile(const fab_flow_desc& f, long long n, bool with_grad, StateFn state_floats,
               TileLayout* out) {
     const int cands[4] = {16, 14, 8, 4};
+    static const int forced = getenv("FAB_FORCE_TILE") ? atoi(getenv("FAB_FORCE_TILE")) : 0;
     long long best_cost = -1; int best = 0;
     for (int c = 0; c < 4; ++c) {
         const int T = cands[c];
+        if (forced && T != forced) continue;
         TileLayout L = make_tile_layout(f, T, with_grad, state_floats(T, fab_round4(f.dim)));
-        if ((long long)L.total_floats * 4 > kMaxSmemBytes) continue;
+        const long long bytes = (long long)L.total_floats * 4;
+        if (bytes > kMaxSmemBytes) continue;
+        // CTAs that fit an SM together (shared memory: 228 KB per SM, 1 KB reserved per CTA;
+        // registers: FAB_MIN_CTAS in __launch_bounds__) overlap each other's serial phases
+        long long per_sm = (228 * 1024) / (bytes + 1024);
+        if (per_sm > FAB_MIN_CTAS) per_sm = FAB_MIN_CTAS;
+        if (per_sm < 1) per_sm = 1;
         const long long ctas = (n + T - 1) / T;
-        const long long waves = (ctas + sm_count() - 1) / sm_count();
-        const long long cost = waves * T;
+        const long long slots = (long long)sm_count() * per_sm;
+        const long long waves = (ctas + slots - 1) / slots;
+        // time ~ particles an SM has to carry one after the other
+        const long long on_sm = ctas < slots ? (ctas + sm_count() - 1) / sm_count() : per_sm;
+        const long long cost = waves * on_sm * T;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = T; *out = L; }
     }
     return best;

@@ -12,10 +12,10 @@
 //                       u' = [v1,y2];           log q += sum(log_S) - sum(scale)
 // Per layer and direction this is three GEMMs (include/fab_b200.h: o_mw1/o_w2/o_w3 and
 // o_w3t/o_w2t/o_w1mt): the mixing matrix is merged into the neighbouring MLP GEMM and biases ride
-// along as an extra K row against a constant-one activation block.
+// along as an extra K row against a constant-one activation row.
 //
-// zs, vs, z1b, par, h1, h2 are GEMM operands in the k4-major layout (tile_gemm.cuh): element
-// (p, n) of any of them sits at float index kidx<T>(p, n), independent of the buffer width.
+// zs, vs, z1b, par, h1, h2 are GEMM operands in the k-major / particle-fastest layout
+// (tile_gemm.cuh): element (p, n) of any of them sits at float index kidx<T>(p, n) = n*TP + p.
 #pragma once
 #include "tile_gemm.cuh"
 
@@ -37,26 +37,28 @@ __device__ __forceinline__ TileBufs tile_bufs(const TileLayout& L, float* smem) 
     return b;
 }
 
+// rows [row, row+4) of an operand buffer := (1,0,0,0) pattern: the constant activation that
+// multiplies the bias row of an operand
 template <int T>
-__device__ __forceinline__ void set_one_block(float* buf, int k4_block) {
-    // the constant (1,0,0,0) activation block that multiplies the bias row of an operand
-    for (int p = threadIdx.x; p < T; p += FAB_NT)
-        reinterpret_cast<float4*>(buf)[(size_t)k4_block * T + p] = make_float4(1.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ void set_one_rows(float* buf, int row) {
+    constexpr int TP = TileDims<T>::TP;
+    for (int i = threadIdx.x; i < 4 * TP; i += FAB_NT) buf[(size_t)row * TP + i] = i < TP ? 1.f : 0.f;
 }
 
 // Once per kernel: zero the operand buffers (pad rows/columns must stay exactly 0 because the
-// packed weights multiply them by 0 and 0*inf would poison a row), set the bias blocks, and stage
+// packed weights multiply them by 0 and 0*inf would poison a row), set the bias rows, and stage
 // the small per-flow constants (base loc / log_scale, per-layer sum(log_S)) in shared memory so
 // that no serial code path waits on an L2 round trip.
 template <int T>
 __device__ __forceinline__ void tile_init(const TileLayout& L, const TileBufs& b,
                                           const fab_flow_desc& f, const float* __restrict__ blob) {
-    for (int i = threadIdx.x; i < T * (L.DP + 4); i += FAB_NT) b.zs[i] = 0.f;
-    for (int i = threadIdx.x; i < T * L.DP; i += FAB_NT) b.vs[i] = 0.f;
-    for (int i = threadIdx.x; i < T * (L.D1P + 4); i += FAB_NT) b.z1b[i] = 0.f;
-    for (int i = threadIdx.x; i < T * L.P2; i += FAB_NT) b.par[i] = 0.f;
-    for (int i = threadIdx.x; i < T * (L.WP + (L.DP > 4 ? L.DP : 4)); i += FAB_NT) b.h1[i] = 0.f;
-    for (int i = threadIdx.x; i < T * (L.WP + 4); i += FAB_NT) b.h2[i] = 0.f;
+    constexpr int TP = TileDims<T>::TP;
+    for (int i = threadIdx.x; i < TP * (L.DP + 4); i += FAB_NT) b.zs[i] = 0.f;
+    for (int i = threadIdx.x; i < TP * L.DP; i += FAB_NT) b.vs[i] = 0.f;
+    for (int i = threadIdx.x; i < TP * (L.D1P + 4); i += FAB_NT) b.z1b[i] = 0.f;
+    for (int i = threadIdx.x; i < TP * L.P2; i += FAB_NT) b.par[i] = 0.f;
+    for (int i = threadIdx.x; i < TP * (L.WP + (L.DP > 4 ? L.DP : 4)); i += FAB_NT) b.h1[i] = 0.f;
+    for (int i = threadIdx.x; i < TP * (L.WP + 4); i += FAB_NT) b.h2[i] = 0.f;
     for (int j = threadIdx.x; j < L.DP; j += FAB_NT) {
         const float loc = j < L.d ? __ldg(blob + f.off_base_loc + j) : 0.f;
         const float ls = j < L.d ? __ldg(blob + f.off_base_log_scale + j) : 0.f;
@@ -65,46 +67,50 @@ __device__ __forceinline__ void tile_init(const TileLayout& L, const TileBufs& b
     for (int k = threadIdx.x; k < L.K; k += FAB_NT)
         b.logs[k] = __ldg(blob + f.off_layers + (size_t)k * f.layer_stride + f.o_logs);
     __syncthreads();
-    set_one_block<T>(b.zs, L.DP / 4);
-    set_one_block<T>(b.z1b, L.D1P / 4);
-    set_one_block<T>(b.h1, L.WP / 4);
-    set_one_block<T>(b.h2, L.WP / 4);
+    set_one_rows<T>(b.zs, L.DP);
+    set_one_rows<T>(b.z1b, L.D1P);
+    set_one_rows<T>(b.h1, L.WP);
+    set_one_rows<T>(b.h2, L.WP);
     __syncthreads();
 }
 
-// hidden-layer epilogue, one float4 (4 consecutive columns of one particle) per lane and step:
-// FWD: h = relu(sum)  (bias already inside the GEMM), ReLU masks = 4 ballots per 32 float4;
+// hidden-layer epilogue; one quad (4 consecutive particles of one column) per lane and step:
+// FWD: h = relu(sum)  (bias already inside the GEMM), ReLU masks = 4 ballots per 32 quads;
 // BWD: h = mask ? sum : 0.   `col0` = first column of this block inside the GEMM output.
 template <int T, bool FWD, bool SAVE>
 __device__ __forceinline__ void hidden_epilogue(const TileLayout& L, const float* red, int KS,
                                                 int NP, int col0, float* h, uint32_t* mask) {
+    constexpr int TP = TileDims<T>::TP;
+    constexpr int QP = TP / 4;                     // quads per column
     const int lane = threadIdx.x & 31;
-    const int nq = T * (L.WP >> 2);
+    const int nq = L.WP * QP;
     float4* h4 = reinterpret_cast<float4*>(h);
     for (int q0 = (threadIdx.x & ~31); q0 < nq; q0 += FAB_NT) {
         const int q = q0 + lane;
         const bool in = q < nq;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (in) {
-            const int k4 = q / T;
-            const int p = q - k4 * T;
-            v = red_sum4<T>(red, KS, NP, p, col0 + (k4 << 2));
+            const int n = q / QP;
+            const int p0 = (q - n * QP) << 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (p0 + i < T) v[i] = red_sum<T>(red, KS, NP, p0 + i, col0 + n);
         }
         uint32_t* mw = mask + ((q0 >> 5) << 2);
         if (FWD) {
-            const bool px = in && v.x > 0.f, py = in && v.y > 0.f, pz = in && v.z > 0.f,
-                       pw = in && v.w > 0.f;
+            const bool px = in && v[0] > 0.f, py = in && v[1] > 0.f, pz = in && v[2] > 0.f,
+                       pw = in && v[3] > 0.f;
             if (SAVE) {
                 const uint32_t bx = __ballot_sync(FAB_FULL, px), by = __ballot_sync(FAB_FULL, py),
                                bz = __ballot_sync(FAB_FULL, pz), bw = __ballot_sync(FAB_FULL, pw);
                 if (lane == 0) *reinterpret_cast<uint4*>(mw) = make_uint4(bx, by, bz, bw);
             }
-            if (in) h4[q] = make_float4(px ? v.x : 0.f, py ? v.y : 0.f, pz ? v.z : 0.f, pw ? v.w : 0.f);
+            if (in) h4[q] = make_float4(px ? v[0] : 0.f, py ? v[1] : 0.f, pz ? v[2] : 0.f, pw ? v[3] : 0.f);
         } else {
             const uint4 bits = *reinterpret_cast<const uint4*>(mw);
             if (in)
-                h4[q] = make_float4((bits.x >> lane) & 1u ? v.x : 0.f, (bits.y >> lane) & 1u ? v.y : 0.f,
-                                    (bits.z >> lane) & 1u ? v.z : 0.f, (bits.w >> lane) & 1u ? v.w : 0.f);
+                h4[q] = make_float4((bits.x >> lane) & 1u ? v[0] : 0.f, (bits.y >> lane) & 1u ? v[1] : 0.f,
+                                    (bits.z >> lane) & 1u ? v[2] : 0.f, (bits.w >> lane) & 1u ? v[3] : 0.f);
         }
     }
 }
@@ -150,6 +156,7 @@ __device__ __forceinline__ void logdet_accumulate(const TileLayout& L, const Til
 template <int T, bool SAVE>
 __device__ void flow_inverse(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                              const float* __restrict__ blob, float* lq_out) {
+    constexpr int TP = TileDims<T>::TP;
     for (int p = threadIdx.x; p < T; p += FAB_NT) b.ld[p] = 0.f;
     const int NP1 = L.DP + L.WP;
     for (int k = L.K - 1; k >= 0; --k) {
@@ -160,10 +167,10 @@ __device__ void flow_inverse(const TileLayout& L, const TileBufs& b, const fab_f
         tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
                               L.red_floats);
         __syncthreads();
-        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+        for (int e = threadIdx.x; e < TP * L.d; e += FAB_NT) {
             int p, n;
             kdecode<T>(e, p, n);
-            if (n < L.d) {
+            if (p < T) {
                 const float v = red_sum<T>(b.red, KS, NP1, p, n);
                 b.vs[e] = v;
                 if (n < L.d1) b.zs[e] = v;
@@ -171,7 +178,7 @@ __device__ void flow_inverse(const TileLayout& L, const TileBufs& b, const fab_f
         }
         hidden_epilogue<T, true, SAVE>(L, b.red, KS, NP1, L.DP, b.h1,
                                        SAVE ? b.m1 + (size_t)k * L.MW : nullptr);
-        if (SAVE) set_one_block<T>(b.h1, L.WP / 4);   // flow_backward parks [gv] in these blocks
+        if (SAVE) set_one_rows<T>(b.h1, L.WP);        // flow_backward parks [gv] in these rows
         __syncthreads();
         KS = mlp_tail<T, SAVE>(L, b, lay, f, k, k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr,
                                L.DP / 4 + 1, NP1);
@@ -219,8 +226,9 @@ __device__ void flow_inverse(const TileLayout& L, const TileBufs& b, const fab_f
 template <int T>
 __device__ void flow_backward(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                               const float* __restrict__ blob) {
+    constexpr int TP = TileDims<T>::TP;
     float* gs = b.vs;
-    float* gv = b.h1 + (size_t)(L.WP / 4) * T * 4;     // [gv] blocks behind gh1 (k4-major)
+    float* gv = b.h1 + (size_t)L.WP * TP;               // [gv] rows behind gh1
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
         // coupling backward: gv2 = g2*es, gshift = -gv2, gscale = -g2*y2 - 1
@@ -235,10 +243,10 @@ __device__ void flow_backward(const TileLayout& L, const TileBufs& b, const fab_
             b.par[kidx<T>(p, L.d2 + j)] = -g2 * y2 - 1.0f;
             gv[e] = gv2;
         }
-        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+        for (int e = threadIdx.x; e < TP * L.DP; e += FAB_NT) {
             int p, n;
             kdecode<T>(e, p, n);
-            if (n < L.d1) gv[e] = gs[e];
+            if (n < L.d1) gv[e] = p < T ? gs[e] : 0.f;
             else if (n >= L.d) gv[e] = 0.f;
         }
         __syncthreads();
@@ -266,10 +274,10 @@ __device__ void flow_backward(const TileLayout& L, const TileBufs& b, const fab_
                                   reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t),
                                   L.WP, L.red_floats);
         __syncthreads();
-        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+        for (int e = threadIdx.x; e < TP * L.d; e += FAB_NT) {
             int p, n;
             kdecode<T>(e, p, n);
-            if (n < L.d) gs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
+            if (p < T) gs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
         }
         __syncthreads();
     }
@@ -279,6 +287,7 @@ __device__ void flow_backward(const TileLayout& L, const TileBufs& b, const fab_
 template <int T>
 __device__ void flow_sample(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
                             const float* __restrict__ blob, float* lq_out) {
+    constexpr int TP = TileDims<T>::TP;
     {   // base: z = loc + exp(log_scale)*eps ; log p0 = -d/2 log 2pi - sum(log_scale + eps^2/2)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int p = warp; p < T; p += FAB_NWARPS) {
@@ -294,15 +303,11 @@ __device__ void flow_sample(const TileLayout& L, const TileBufs& b, const fab_fl
             if (lane == 0) b.ld[p] = -0.5f * (float)L.d * 1.8378770664093453f - s;
         }
     }
-    set_one_block<T>(b.h1, L.WP / 4);
+    set_one_rows<T>(b.h1, L.WP);
     __syncthreads();
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
-        for (int e = threadIdx.x; e < T * L.D1P; e += FAB_NT) {
-            int p, n;
-            kdecode<T>(e, p, n);
-            if (n < L.d1) b.z1b[e] = b.zs[e];
-        }
+        for (int e = threadIdx.x; e < TP * L.d1; e += FAB_NT) b.z1b[e] = b.zs[e];
         __syncthreads();
         int KS = tile_gemm<T>(b.z1b, L.D1P / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w1),
                               L.WP, b.red, L.red_floats);
@@ -331,10 +336,10 @@ __device__ void flow_sample(const TileLayout& L, const TileBufs& b, const fab_fl
                                   reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w1),
                                   L.WP, L.red_floats);
         __syncthreads();
-        for (int e = threadIdx.x; e < T * L.DP; e += FAB_NT) {
+        for (int e = threadIdx.x; e < TP * L.d; e += FAB_NT) {
             int p, n;
             kdecode<T>(e, p, n);
-            if (n < L.d) b.zs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
+            if (p < T) b.zs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
         }
         __syncthreads();
     }

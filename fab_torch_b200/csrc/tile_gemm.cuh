@@ -1,47 +1,61 @@
 // Tile GEMM: out[p][n] = sum_k act[p][k] * M[k][n] for the T particles of one CTA.
 //
-//   act : shared memory, "k4-major" operand layout  float4 act4[K4][T]  (act4[k4][p] holds
-//         act[p][4*k4 .. 4*k4+3]); element (p,k) lives at float index kidx<T>(p,k).  With T a
-//         compile-time constant every LDS.128 of the inner loop has an immediate offset.
-//         Biases are part of the operand: the last k4 block of `act` is the constant (1,0,0,0)
-//         and the matching weight rows hold (bias,0,0,0) -- see include/fab_b200.h.
+//   act : shared memory operand, k-major with particles fastest:  act[k][TP]  (TP = T rounded up
+//         to 4), element (p,k) at float index kidx<T>(p,k) = k*TP + p.  One LDS.128 therefore
+//         yields two *particle pairs* of one k, ready as the packed operands of fma.rn.f32x2.
+//         Biases are part of the operand: after the K real rows comes a row of ones (then three
+//         zero rows) and the matching weight rows hold (bias,0,0,0) -- see include/fab_b200.h.
 //   Wp  : global (L2-resident) packed operand, float4 [K4][NP]
-//   red : shared reduction buffer [KS][T][NP+4] (row padded by 4 floats so that the fused
-//         epilogues, which walk particles fastest, read it without bank conflicts)
+//   red : shared reduction buffer [KS][T][NP+4] (row padded by 4 floats: conflict-free for the
+//         fused epilogues)
 //
 // Work decomposition.  A *unit* is (k-split ks, column group ng); it owns the FAB_TN output
 // columns n_t = ng + t*NP/FAB_TN for ALL T particles over the k-range of its split, i.e.
-// FAB_TN*T fp32 accumulators in registers.  Each packed weight word is therefore loaded from L2
-// exactly once per CTA, by exactly one thread, straight into registers (coalesced: consecutive ng
-// read consecutive float4; non-allocating so the stream does not evict the small L1-resident
-// tables), and activations are read with warp-broadcast LDS.128.  Per 4-wide k step a unit issues
-// FAB_TN LDG.128 + T LDS.128 + 4*FAB_TN*T FFMA.  Weight loads run FAB_PF steps ahead in a register
-// ring; the steady-state loop is branch-free.
+// FAB_TN*T fp32 accumulators held as FAB_TN*T/2 packed pairs.  Each packed weight word is loaded
+// from L2 exactly once per CTA, by exactly one thread, straight into registers (coalesced,
+// non-allocating), and activations are read with warp-broadcast LDS.128.  The inner product runs
+// on Blackwell's packed FP32 pipe: per 4-wide k step a unit issues FAB_TN LDG.128 + ~TP LDS.128 +
+// 2*FAB_TN*T FFMA2 (fma.rn.f32x2, two particles per instruction), which halves the issue slots
+// per FLOP -- measured on B200 (profiles/microbench_ffma.cu) this loop sustains 80-84 % of the
+// 74.4 TFLOP/s FP32 peak versus 60 % for scalar FFMA.  Weight loads run FAB_PF steps ahead in a
+// register ring; the steady-state loop is branch-free.
 // tile_gemm_prefetch() pulls the first weight tiles of the NEXT GEMM into L1 while the current
 // epilogue runs, hiding the L2 latency that would otherwise be exposed after every barrier.
 //
-// Roofline: FP32 FFMA pipe (tensor cores cannot hold the 1e-5-relative fp32 parity bar in one
+// Roofline: FP32 FMA pipe (tensor cores cannot hold the 1e-5-relative fp32 parity bar in one
 // pass, and at <= 2048 particles per GPU a 128-row UMMA tile would leave 132 of 148 SMs idle;
 // see DESIGN.md §4).
 #pragma once
 #include "common.cuh"
 
-#ifndef FAB_TN
-#define FAB_TN 4   // output columns per unit
-#endif
 #ifndef FAB_PF
 #define FAB_PF 2   // weight prefetch distance in k4 steps
 #endif
 
+typedef unsigned long long fab_u64;
+__device__ __forceinline__ fab_u64 pack2(float a, float b) {
+    fab_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(fab_u64 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ fab_u64 ffma2(fab_u64 a, fab_u64 b, fab_u64 c) {
+    fab_u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+template <int T> struct TileDims { static constexpr int TP = (T + 3) & ~3; };
+
 template <int T>
-__device__ __forceinline__ int kidx(int p, int n) { return (((n >> 2) * T + p) << 2) | (n & 3); }
-// inverse of kidx for a linear element index e of a k4-major buffer
+__device__ __forceinline__ int kidx(int p, int n) { return n * TileDims<T>::TP + p; }
+// inverse of kidx for a linear element index e of an operand buffer (p may be a pad slot >= T)
 template <int T>
 __device__ __forceinline__ void kdecode(int e, int& p, int& n) {
-    const int q = e >> 2;              // float4 index = k4*T + p
-    const int k4 = q / T;
-    p = q - k4 * T;
-    n = (k4 << 2) | (e & 3);
+    n = e / TileDims<T>::TP;
+    p = e - n * TileDims<T>::TP;
 }
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
@@ -67,35 +81,34 @@ __device__ __forceinline__ GemmPlan gemm_plan(int K4, int NP, int red_floats) {
     return g;
 }
 
+// one 4-wide k step: acc[q][t] (+)= (act[2q][k], act[2q+1][k]) * (w_t[k], w_t[k]) for 4 k's
 template <int T>
-__device__ __forceinline__ void gemm_step(float (&acc)[T][FAB_TN], const float4* a4,
+__device__ __forceinline__ void gemm_step(fab_u64 (&acc)[T / 2][FAB_TN], const float* a,
                                           const float4 (&w)[FAB_TN]) {
+    constexpr int TP = TileDims<T>::TP;
+    constexpr int NQ = T / 2;                       // particle pairs
 #pragma unroll
-    for (int p = 0; p + 1 < T; p += 2) {
-        const float4 a0 = a4[p];
-        const float4 a1 = a4[p + 1];
-        // component-major over the pair: 2*FAB_TN independent FFMAs between dependent ones
+    for (int c = 0; c < 4; ++c) {
+        fab_u64 w2[FAB_TN];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float x0 = c == 0 ? a0.x : c == 1 ? a0.y : c == 2 ? a0.z : a0.w;
-            const float x1 = c == 0 ? a1.x : c == 1 ? a1.y : c == 2 ? a1.z : a1.w;
-#pragma unroll
-            for (int t = 0; t < FAB_TN; ++t) {
-                const float wv = c == 0 ? w[t].x : c == 1 ? w[t].y : c == 2 ? w[t].z : w[t].w;
-                acc[p][t] = fmaf(x0, wv, acc[p][t]);
-                acc[p + 1][t] = fmaf(x1, wv, acc[p + 1][t]);
-            }
+        for (int t = 0; t < FAB_TN; ++t) {
+            const float wv = c == 0 ? w[t].x : c == 1 ? w[t].y : c == 2 ? w[t].z : w[t].w;
+            w2[t] = pack2(wv, wv);
         }
-    }
-    if (T & 1) {
-        const float4 a0 = a4[T - 1];
+        const fab_u64* arow = reinterpret_cast<const fab_u64*>(a + c * TP);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float x0 = c == 0 ? a0.x : c == 1 ? a0.y : c == 2 ? a0.z : a0.w;
+        for (int q = 0; q < NQ; q += 2) {
+            fab_u64 p0, p1 = 0;
+            if (q + 1 < NQ) {                       // LDS.128: two pairs
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(arow + q);
+                p0 = v.x; p1 = v.y;
+            } else {                                // trailing pair: LDS.64
+                p0 = arow[q];
+            }
 #pragma unroll
             for (int t = 0; t < FAB_TN; ++t) {
-                const float wv = c == 0 ? w[t].x : c == 1 ? w[t].y : c == 2 ? w[t].z : w[t].w;
-                acc[T - 1][t] = fmaf(x0, wv, acc[T - 1][t]);
+                acc[q][t] = ffma2(p0, w2[t], acc[q][t]);
+                if (q + 1 < NQ) acc[q + 1][t] = ffma2(p1, w2[t], acc[q + 1][t]);
             }
         }
     }
@@ -127,6 +140,8 @@ __device__ __forceinline__ void tile_gemm_prefetch(int K4, const float4* __restr
 template <int T>
 __device__ __noinline__ int tile_gemm(const float* act, int K4, const float4* __restrict__ Wp,
                                       int NP, float* red, int red_floats) {
+    static_assert(T % 2 == 0, "particles are processed in pairs");
+    constexpr int TP = TileDims<T>::TP;
     const GemmPlan g = gemm_plan<T>(K4, NP, red_floats);
     const int NG = g.NG;
     const int NPs = NP + 4;
@@ -137,14 +152,14 @@ __device__ __noinline__ int tile_gemm(const float* act, int K4, const float4* __
         const int k4b = ks * g.ksteps;
         int nsteps = K4 - k4b;
         if (nsteps > g.ksteps) nsteps = g.ksteps;
-        float acc[T][FAB_TN];
+        fab_u64 acc[T / 2][FAB_TN];
 #pragma unroll
-        for (int p = 0; p < T; ++p)
+        for (int q = 0; q < T / 2; ++q)
 #pragma unroll
-            for (int t = 0; t < FAB_TN; ++t) acc[p][t] = 0.f;
+            for (int t = 0; t < FAB_TN; ++t) acc[q][t] = 0ull;
         if (nsteps > 0) {
             const float4* wp = Wp + (size_t)k4b * NP + ng;          // column t: + t*NG
-            const float4* a4 = reinterpret_cast<const float4*>(act) + (size_t)k4b * T;
+            const float* a = act + (size_t)k4b * 4 * TP;
             float4 ring[FAB_PF][FAB_TN];
 #pragma unroll
             for (int i = 0; i < FAB_PF; ++i) {
@@ -165,7 +180,7 @@ __device__ __noinline__ int tile_gemm(const float* act, int K4, const float4* __
                         w[t] = ring[i][t];
                         ring[i][t] = ldg_stream(wp + (size_t)(s + i + FAB_PF) * NP + t * NG);
                     }
-                    gemm_step<T>(acc, a4 + (size_t)(s + i) * T, w);
+                    gemm_step<T>(acc, a + (size_t)(s + i) * 4 * TP, w);
                 }
             }
             // tail: fewer than 2*FAB_PF steps left
@@ -181,21 +196,26 @@ __device__ __noinline__ int tile_gemm(const float* act, int K4, const float4* __
                             for (int t = 0; t < FAB_TN; ++t)
                                 ring[i][t] = ldg_stream(wp + (size_t)(s + i + FAB_PF) * NP + t * NG);
                         }
-                        gemm_step<T>(acc, a4 + (size_t)(s + i) * T, w);
+                        gemm_step<T>(acc, a + (size_t)(s + i) * 4 * TP, w);
                     }
                 }
             }
         }
         float* r = red + (size_t)ks * T * NPs + ng;
 #pragma unroll
-        for (int p = 0; p < T; ++p)
+        for (int q = 0; q < T / 2; ++q)
 #pragma unroll
-            for (int t = 0; t < FAB_TN; ++t) r[p * NPs + t * NG] = acc[p][t];
+            for (int t = 0; t < FAB_TN; ++t) {
+                float lo, hi;
+                unpack2(acc[q][t], lo, hi);
+                r[(2 * q) * NPs + t * NG] = lo;
+                r[(2 * q + 1) * NPs + t * NG] = hi;
+            }
     }
     return g.KS;
 }
 
-// sum of the k-split partials of one output element / of four consecutive columns
+// sum of the k-split partials of one output element
 template <int T>
 __device__ __forceinline__ float red_sum(const float* red, int KS, int NP, int p, int n) {
     const int NPs = NP + 4;
@@ -204,19 +224,5 @@ __device__ __forceinline__ float red_sum(const float* red, int KS, int NP, int p
     const int stride = T * NPs;
 #pragma unroll 4
     for (int ks = 1; ks < KS; ++ks) { r += stride; s += r[0]; }
-    return s;
-}
-template <int T>
-__device__ __forceinline__ float4 red_sum4(const float* red, int KS, int NP, int p, int n0) {
-    const int NPs = NP + 4;
-    const float* r = red + p * NPs + n0;
-    float4 s = *reinterpret_cast<const float4*>(r);
-    const int stride = T * NPs;
-#pragma unroll 4
-    for (int ks = 1; ks < KS; ++ks) {
-        r += stride;
-        const float4 v = *reinterpret_cast<const float4*>(r);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
     return s;
 }

