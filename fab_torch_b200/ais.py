@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from fab_torch_b200 import _lib
+from fab_torch_b200 import dist as fdist
 from fab_torch_b200.point import Point
 from fab_torch_b200.transition_operators import TransitionOperator, make_gamma
 
@@ -83,10 +84,7 @@ class AnnealedImportanceSampler:
         return logging_info
 
     def _world(self):
-        if self.process_group is None:
-            return 1, 0
-        import torch.distributed as dist
-        return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+        return fdist.world(self.process_group)
 
     def _filter(self, pt: Point, log_w, n_in, n_out):
         L = _lib.lib()
@@ -110,12 +108,7 @@ class AnnealedImportanceSampler:
                                    values.shape[0], _lib.ptr(n_active), _lib.ptr(part),
                                    _lib.stream_ptr(dev))
         _lib.check(rc, "fab_ess_partial_f32")
-        if world > 1:
-            import torch.distributed as dist
-            parts = torch.empty(4 * world, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(parts, part, group=self.process_group)
-        else:
-            parts = part
+        parts = fdist.gather_partials(part, self.process_group)
         rc = L.fab_ess_finalize_f32(_lib.ptr(parts), world, _lib.ptr(out3), _lib.stream_ptr(dev))
         _lib.check(rc, "fab_ess_finalize_f32")
 
@@ -177,7 +170,7 @@ class AnnealedImportanceSampler:
         """Mean device time (ms) of one fused transition launch, measured with CUDA events on the
         launching stream around every transition of `repeats` chains (bench.py roofline)."""
         world, rank = self._world()
-        local = batch_size // world
+        local = fdist.shard_size(batch_size, self.process_group)
         self.transition_operator.process_group = self.process_group
         total, count = 0.0, 0
         for _ in range(repeats):
@@ -193,10 +186,7 @@ class AnnealedImportanceSampler:
         world, rank = self._world()
         op = self.transition_operator
         op.process_group = self.process_group
-        local = batch_size
-        if world > 1:
-            assert batch_size % world == 0, "batch_size must be divisible by the world size"
-            local = batch_size // world
+        local = fdist.shard_size(batch_size, self.process_group)
         pt, log_w, counts, rec = self._run_chain(local, logging)
         dev = log_w.device
         if self._host is None:

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from fab_torch_b200 import _lib
+from fab_torch_b200 import dist as fdist
 from fab_torch_b200.point import Point
 from fab_torch_b200.types_ import LogProbFunc
 
@@ -157,10 +158,7 @@ class TransitionOperator(nn.Module):
         return self._ws
 
     def _world(self) -> int:
-        if self.process_group is None:
-            return 1
-        import torch.distributed as dist
-        return dist.get_world_size(self.process_group)
+        return fdist.world(self.process_group)[0]
 
     @staticmethod
     def _check_point(point: Point, need_grad: bool):
@@ -319,8 +317,7 @@ class HamiltonianMonteCarlo(TransitionOperator):
                                     _lib.ptr(self._stats), _lib.ptr(ws), n, stream)
             _lib.check(rc, "fab_hmc_step_f32")
             if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self._stats[:4], op=dist.ReduceOp.SUM, group=self.process_group)
+                fdist.reduce_stats(self._stats[:4], self.process_group)
                 _lib.check(L.fab_hmc_finish_f32(st, args, _lib.ptr(self._stats), stream),
                            "fab_hmc_finish_f32")
             prop_in = prop_out
@@ -410,8 +407,7 @@ class Metropolis(TransitionOperator):
                                              _lib.ptr(self._stats), _lib.ptr(ws), n, stream)
         _lib.check(rc, "fab_metropolis_transition_f32")
         if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._stats, op=dist.ReduceOp.SUM, group=self.process_group)
+            fdist.reduce_stats(self._stats, self.process_group)
             _lib.check(L.fab_metropolis_finish_f32(args, _lib.ptr(self.noise_scalings),
                                                    _lib.ptr(self._stats), stream),
                        "fab_metropolis_finish_f32")

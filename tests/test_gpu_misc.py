@@ -1,0 +1,127 @@
+"""GPU: the small kernels around the transitions -- ESS / log Z reduction, NaN/inf filter,
+log-weight update, systematic resampling (bit-exact against oracle/resample.py)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import fab_torch_b200 as fb
+from fab_torch_b200 import _lib, dist as fdist
+from oracle.resample import systematic_ancestors as oracle_ancestors, fixed_point_weights
+from oracle.sampler import effective_sample_size as oracle_ess, gamma as oracle_gamma, Point as OPoint, beta_schedule
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 31, 2048, 100003])
+def test_effective_sample_size(n):
+    g = torch.Generator().manual_seed(n)
+    lw = torch.randn(n, generator=g) * 5 + 300.0
+    got = fb.effective_sample_size(lw.cuda())
+    want = oracle_ess(lw.double())
+    assert abs(got.item() - want.item()) <= 1e-5 * want.item()
+    # normalised=True branch (numerical.py:21-23)
+    w = torch.softmax(lw, 0)
+    assert abs(fb.effective_sample_size(w.cuda(), normalised=True).item() - want.item()) <= 1e-4 * want.item()
+
+
+def test_ess_partials_merge_like_multi_gpu():
+    """Two 'ranks' on one device: partial quadruples merged by the kernel == single-shot result."""
+    L = _lib.lib()
+    lw = (torch.randn(4096) * 3 - 50).cuda()
+    halves = [lw[:1000].contiguous(), lw[1000:].contiguous()]
+    parts = torch.empty(8, device="cuda")
+    for r, h in enumerate(halves):
+        _lib.check(L.fab_ess_partial_f32(_lib.ptr(h), None, h.shape[0], None,
+                                         _lib.ptr(parts[4 * r:4 * r + 4]), _lib.stream_ptr()))
+    out = torch.empty(3, device="cuda")
+    _lib.check(L.fab_ess_finalize_f32(_lib.ptr(parts), 2, _lib.ptr(out), _lib.stream_ptr()))
+    want = oracle_ess(lw.cpu().double()).item()
+    assert abs(out[0].item() - want) <= 1e-5 * want
+    assert abs(out[1].item() - torch.logsumexp(lw.cpu().double(), 0).item()) < 1e-4
+    assert out[2].item() == 4096
+    ess_t, lse_t, cnt_t = fdist.merge_ess_partials(parts.cpu())       # host restatement agrees
+    assert abs(float(ess_t) - out[0].item()) <= 1e-5 * want and int(cnt_t) == 4096
+
+
+def test_nan_filter_compacts_in_order():
+    L = _lib.lib()
+    n, d = 1000, 5
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, d, generator=g)
+    lq, lp, lw = torch.randn(n, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g)
+    gq, gp = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+    bad = torch.zeros(n, dtype=torch.bool)
+    bad[torch.randperm(n, generator=g)[:137]] = True
+    lq[bad & (torch.arange(n) % 3 == 0)] = float("nan")
+    lp[bad & (torch.arange(n) % 3 == 1)] = float("inf")
+    lp[bad & (torch.arange(n) % 3 == 2)] = -float("inf")
+    keep = torch.isfinite(lq) & torch.isfinite(lp)
+    pt = fb.Point(x.cuda(), lq.cuda(), lp.cuda(), gq.cuda(), gp.cuda())
+    lwc = lw.cuda()
+    ws = torch.empty(int(L.fab_filter_workspace_bytes(n, d)), dtype=torch.uint8, device="cuda")
+    n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.fab_nan_filter_f32(_lib.point_ptrs(pt), _lib.ptr(lwc), d, n, None, _lib.ptr(n_out),
+                                    _lib.ptr(ws), _lib.stream_ptr()))
+    m = int(n_out.item())
+    assert m == int(keep.sum())
+    assert torch.equal(pt.x[:m].cpu(), x[keep]) and torch.equal(pt.log_q[:m].cpu(), lq[keep])
+    assert torch.equal(pt.log_p[:m].cpu(), lp[keep]) and torch.equal(lwc[:m].cpu(), lw[keep])
+    assert torch.equal(pt.grad_log_q[:m].cpu(), gq[keep]) and torch.equal(pt.grad_log_p[:m].cpu(), gp[keep])
+    # second pass on the compacted prefix (device-side count as input) is a no-op
+    n_out2 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.fab_nan_filter_f32(_lib.point_ptrs(pt), _lib.ptr(lwc), d, n, _lib.ptr(n_out),
+                                    _lib.ptr(n_out2), _lib.ptr(ws), _lib.stream_ptr()))
+    assert int(n_out2.item()) == m and torch.equal(pt.x[:m].cpu(), x[keep])
+
+
+@pytest.mark.parametrize("p_target,alpha", [(True, None), (False, 2.0), (False, 0.5)])
+def test_logw_update_is_bit_exact(p_target, alpha):
+    """K11 (ais.py:93-100): same fp32 op sequence as torch -> identical bits."""
+    L = _lib.lib()
+    n = 5000
+    lq, lp, lw = torch.randn(n) * 50 - 100, torch.randn(n) * 30 - 20, torch.randn(n) * 10
+    B = beta_schedule("linear", 16)
+    j = 7
+    pt = OPoint(None, lq, lp)
+    want = lw + (oracle_gamma(pt, B[j + 1], alpha, p_target) - oracle_gamma(pt, B[j], alpha, p_target))
+    lwc = lw.cuda()
+    _lib.check(L.fab_logw_update_f32(fb.make_gamma(B[j], alpha, p_target),
+                                     fb.make_gamma(B[j + 1], alpha, p_target),
+                                     _lib.ptr(lq.cuda()), _lib.ptr(lp.cuda()), _lib.ptr(lwc), n,
+                                     _lib.stream_ptr()))
+    assert torch.equal(lwc.cpu(), want)
+
+
+@pytest.mark.parametrize("n", [1, 7, 512, 2048, 16384])
+@pytest.mark.parametrize("spread", [0.5, 5.0, 40.0])
+def test_systematic_resample_bit_exact(n, spread):
+    g = torch.Generator().manual_seed(n + int(spread * 10))
+    lw = (torch.randn(n, generator=g) * spread + 123.0)
+    if n > 10:
+        lw[3] = float("nan")
+        lw[5] = -float("inf")
+    for u0 in (0, 1, 2 ** 31 + 12345, 2 ** 32 - 1):
+        want = oracle_ancestors(lw.numpy(), u0)
+        got = fb.systematic_ancestors(lw.cuda(), u0).cpu().numpy()
+        assert np.array_equal(got, want), f"n={n} u0={u0}: {np.flatnonzero(got != want)[:5]}"
+    # resampled particle counts follow the weights: E[count_i] = n * w_i, |count - n w| < 1
+    q = fixed_point_weights(lw.numpy()).astype(np.float64)
+    counts = np.bincount(want, minlength=n)
+    assert np.all(np.abs(counts - n * q / q.sum()) < 1.0 + 1e-9)
+
+
+def test_systematic_resample_point_and_properties():
+    n, d = 4096, 32
+    x = torch.randn(n, d).cuda()
+    pt = fb.Point(x, torch.randn(n).cuda(), torch.randn(n).cuda(), torch.randn(n, d).cuda(),
+                  torch.randn(n, d).cuda())
+    lw = (torch.randn(n) * 3).cuda()
+    new, anc = fb.systematic_resample(pt, lw, u0=987654321)
+    assert torch.equal(new.x, x[anc]) and torch.equal(new.log_q, pt.log_q[anc])
+    assert torch.equal(new.grad_log_p, pt.grad_log_p[anc])
+    assert bool((anc[1:] >= anc[:-1]).all())                      # ancestors are sorted
+    # uniform weights with any offset -> identity permutation (idempotence)
+    anc_u = fb.systematic_ancestors(torch.zeros(n).cuda(), 12345)
+    assert torch.equal(anc_u.cpu(), torch.arange(n))
