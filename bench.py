@@ -47,6 +47,15 @@ def algorithmic_flops_per_particle(cfg):
     return Ff * (1 + 2 * (1 + cfg["M"] * cfg["L"] * cfg["n_outer"]))   # 163 * F_f at config 2
 
 
+def profiled_traffic():
+    """dram__bytes_read+write per k_hmc_step launch from the latest committed ncu capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_metrics.json")))
+    if not files:
+        return None
+    return json.load(open(files[-1])).get("dram_bytes_per_launch")
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -287,7 +296,7 @@ def run_gpu_arm(args):
         n_sm = torch.cuda.get_device_properties(device).multi_processor_count
         ffma_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
         roof = dict(bound="tensor", achieved=achieved, peak=peaks["bf16_tflops_sustained"],
-                    unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"], traffic=None,
+                    unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"], traffic=profiled_traffic(),
                     kernel="k_hmc_step", kernel_ms=kernel_ms, peak_source=peaks["source"] +
                     " bf16_tflops_sustained (kernel timed inside a long step)",
                     pipe="fp32_ffma", pipe_peak=ffma_peak, pipe_frac=achieved / ffma_peak,

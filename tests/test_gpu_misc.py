@@ -86,10 +86,10 @@ def test_logw_update_is_bit_exact(p_target, alpha):
     j = 7
     pt = OPoint(None, lq, lp)
     want = lw + (oracle_gamma(pt, B[j + 1], alpha, p_target) - oracle_gamma(pt, B[j], alpha, p_target))
-    lwc = lw.cuda()
+    lwc, lqc, lpc = lw.cuda(), lq.cuda(), lp.cuda()     # keep the device tensors alive
     _lib.check(L.fab_logw_update_f32(fb.make_gamma(B[j], alpha, p_target),
                                      fb.make_gamma(B[j + 1], alpha, p_target),
-                                     _lib.ptr(lq.cuda()), _lib.ptr(lp.cuda()), _lib.ptr(lwc), n,
+                                     _lib.ptr(lqc), _lib.ptr(lpc), _lib.ptr(lwc), n,
                                      _lib.stream_ptr()))
     assert torch.equal(lwc.cpu(), want)
 
