@@ -81,36 +81,50 @@ template <int T, bool FWD, bool SAVE>
 __device__ __forceinline__ void hidden_epilogue(const TileLayout& L, const float* red, int KS,
                                                 int NP, int col0, float* h, uint32_t* mask) {
     constexpr int TP = TileDims<T>::TP;
-    constexpr int QP = TP / 4;                     // quads per column
+    // work item q = (column quad n4, particle p), particle fastest: the KS partial rows are read
+    // with one LDS.128 each (conflict-free: rows are NP+4 floats apart) and the four results go
+    // to h[4*n4+i][p] (consecutive lanes -> consecutive floats).
     const int lane = threadIdx.x & 31;
-    const int nq = L.WP * QP;
-    float4* h4 = reinterpret_cast<float4*>(h);
+    const int nq = (L.WP >> 2) * T;
+    const int NPs = NP + 4;
+    const int stride = T * NPs;
     for (int q0 = (threadIdx.x & ~31); q0 < nq; q0 += FAB_NT) {
         const int q = q0 + lane;
         const bool in = q < nq;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int n4 = 0, p = 0;
         if (in) {
-            const int n = q / QP;
-            const int p0 = (q - n * QP) << 2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (p0 + i < T) v[i] = red_sum<T>(red, KS, NP, p0 + i, col0 + n);
+            n4 = q / T;
+            p = q - n4 * T;
+            const float* r = red + p * NPs + col0 + (n4 << 2);
+            v = *reinterpret_cast<const float4*>(r);
+#pragma unroll 4
+            for (int ks = 1; ks < KS; ++ks) {
+                r += stride;
+                const float4 u = *reinterpret_cast<const float4*>(r);
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            }
         }
         uint32_t* mw = mask + ((q0 >> 5) << 2);
+        float* hp = h + (size_t)(n4 << 2) * TP + p;
         if (FWD) {
-            const bool px = in && v[0] > 0.f, py = in && v[1] > 0.f, pz = in && v[2] > 0.f,
-                       pw = in && v[3] > 0.f;
+            const bool px = in && v.x > 0.f, py = in && v.y > 0.f, pz = in && v.z > 0.f,
+                       pw = in && v.w > 0.f;
             if (SAVE) {
                 const uint32_t bx = __ballot_sync(FAB_FULL, px), by = __ballot_sync(FAB_FULL, py),
                                bz = __ballot_sync(FAB_FULL, pz), bw = __ballot_sync(FAB_FULL, pw);
                 if (lane == 0) *reinterpret_cast<uint4*>(mw) = make_uint4(bx, by, bz, bw);
             }
-            if (in) h4[q] = make_float4(px ? v[0] : 0.f, py ? v[1] : 0.f, pz ? v[2] : 0.f, pw ? v[3] : 0.f);
+            if (in) {
+                hp[0] = px ? v.x : 0.f; hp[TP] = py ? v.y : 0.f;
+                hp[2 * TP] = pz ? v.z : 0.f; hp[3 * TP] = pw ? v.w : 0.f;
+            }
         } else {
             const uint4 bits = *reinterpret_cast<const uint4*>(mw);
-            if (in)
-                h4[q] = make_float4((bits.x >> lane) & 1u ? v[0] : 0.f, (bits.y >> lane) & 1u ? v[1] : 0.f,
-                                    (bits.z >> lane) & 1u ? v[2] : 0.f, (bits.w >> lane) & 1u ? v[3] : 0.f);
+            if (in) {
+                hp[0] = (bits.x >> lane) & 1u ? v.x : 0.f; hp[TP] = (bits.y >> lane) & 1u ? v.y : 0.f;
+                hp[2 * TP] = (bits.z >> lane) & 1u ? v.z : 0.f; hp[3 * TP] = (bits.w >> lane) & 1u ? v.w : 0.f;
+            }
         }
     }
 }
