@@ -20,13 +20,14 @@ FAB_MAX_UPDATES = 16
 
 class FlowDesc(C.Structure):
     _fields_ = [("dim", C.c_int32), ("d1", C.c_int32), ("d2", C.c_int32), ("width", C.c_int32),
-                ("width_pad", C.c_int32), ("n_layers", C.c_int32),
+                ("width_pad", C.c_int32), ("width_kpad", C.c_int32), ("n_layers", C.c_int32),
                 ("total_floats", C.c_int64),
                 ("off_base_loc", C.c_int64), ("off_base_log_scale", C.c_int64),
                 ("off_layers", C.c_int64), ("layer_stride", C.c_int64),
                 ("o_mw1", C.c_int64), ("o_w2", C.c_int64), ("o_w3", C.c_int64),
                 ("o_w3t", C.c_int64), ("o_w2t", C.c_int64), ("o_w1mt", C.c_int64),
-                ("o_w1", C.c_int64), ("o_mix_inv", C.c_int64), ("o_logs", C.c_int64)]
+                ("o_w1", C.c_int64), ("o_mix_inv", C.c_int64),
+                ("o_b1", C.c_int64), ("o_b2", C.c_int64), ("o_b3", C.c_int64), ("o_logs", C.c_int64)]
 
 
 class TargetDesc(C.Structure):

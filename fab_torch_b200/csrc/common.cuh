@@ -2,91 +2,117 @@
 //
 // Execution model: one thread block ("tile CTA", FAB_NT threads) carries T particles through a
 // whole flow evaluation / HMC outer step with every intermediate in shared memory; only the
-// Point rows and noise touch HBM.  Weights stream from L2 straight into registers (each packed
-// weight word is consumed by exactly one thread of the CTA), see tile_gemm.cuh.
+// Point rows and noise touch HBM.  Weights stream from L2 straight into registers in MMA
+// fragment order (each weight word is consumed by exactly one warp of the CTA), see mma_gemm.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
 #include "fab_b200.h"
 
-#ifndef FAB_NT
-#define FAB_NT 256              // threads per tile CTA (8 warps = 2 per scheduler; best of the sweep in profiles/)
-#endif
+#define FAB_NT 256              // threads per tile CTA: 8 warps, fixed by the warp->tile maps of mma_gemm.cuh
 #ifndef FAB_MIN_CTAS
 #define FAB_MIN_CTAS 1          // co-resident tile CTAs per SM the kernels are compiled for
 #endif
 #define FAB_NWARPS (FAB_NT / 32)
-#ifndef FAB_TN
-#define FAB_TN 4                // output columns per GEMM unit (tile_gemm.cuh)
-#endif
 #define FAB_FULL 0xffffffffu
 
 __host__ __device__ __forceinline__ int fab_round4(int v) { return (v + 3) & ~3; }
 
+// Optional per-phase cycle profile of CTA 0 (-DFAB_PROF; experiment builds only, see
+// profiles/phase_profile.py).  prof_mark(id) charges the cycles since the previous mark to `id`.
+#ifdef FAB_PROF
+__device__ unsigned long long g_fab_prof[32];
+__device__ __forceinline__ void prof_mark(int id) {
+    __shared__ long long s_prof_last;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long t = clock64();
+        if (id >= 0) atomicAdd(&g_fab_prof[id], (unsigned long long)(t - s_prof_last));
+        s_prof_last = t;
+    }
+}
+#else
+__device__ __forceinline__ void prof_mark(int) {}
+#endif
+
 // Shared-memory carve-up of one tile CTA; all offsets in floats.  Filled on the host, passed by
-// value to the kernels (so host and device agree by construction).  zs, vs, z1b, par, h1, h2 are
-// GEMM operands in the k-major / particle-fastest layout of tile_gemm.cuh (act[k][TP], TP = T
-// rounded up to 4); zs, z1b, h1, h2 carry 4 extra rows at the end (the constant-one bias row; for
-// h1 also the [gv] rows of the merged backward GEMM).  Everything else is row-major per particle.
+// value to the kernels (so host and device agree by construction).
+//
+// A CTA carries T <= TP particles in TP "slots" (TP = 16, or 8 for small batches / very wide
+// flows); slot = row of the warp-level MMA tile (mma_gemm.cuh).  zs0/zs1, gs, par, h1, h2 are MMA
+// operands in k-major layout act[k][S] (S = slot stride, 24 floats for TP=16 so that the
+// fragment loads are bank-conflict free, 8 for TP=8); rows are padded to a multiple of 16 (one
+// k-tile pair) and pad rows / pad slots always hold finite values (0 unless an epilogue wrote
+// bias-only garbage into a pad slot).  h1 carries D16 extra rows behind the hidden rows: the
+// [gv] part of the merged backward GEMM.  Everything else is row-major per particle.
 struct TileLayout {
-    int T, TP;          // particles per CTA, rounded up to 4
-    int d, DP;          // dim and round_up(dim,4)
-    int d1, d2, D1P, P2;// conditioner width, transformed width, pads (P2 = round_up(2*d2,4))
-    int WP;             // padded hidden width
+    int T, TP, S;       // particles per CTA, slots (8|16), slot stride of the operand buffers
+    int d, DP;          // dim and round_up(dim,4) (row-major state tiles)
+    int d1, d2;         // conditioner width, transformed width
+    int D8, D16, W8, W16, P8, P16, D1K;   // n-pads (8) / k-pads (16) of d, W, 2*d2; D1K = k-pad of d1
+    int NTH;            // hidden n-tiles = W8/8
     int MW;             // ReLU-mask words per layer and MLP stage
     int K;              // coupling layers
-    int red_floats;     // capacity of the split-K reduction buffer
+    int RS;             // slot stride of the split-K partial buffer
+    int red_floats;     // capacity of the split-K partial buffer
     // offsets
-    int o_zs, o_vs, o_z1b, o_par, o_h1, o_h2, o_red;
+    int o_zs0, o_zs1, o_gs, o_par, o_h1, o_h2, o_red;
     int o_sy2, o_ses, o_m1, o_m2;       // saved-for-backward, [K][...]
-    int o_ld;                           // [T] running log-det
-    int o_scl;                          // [T][d2] coupling scales of the current layer
+    int o_ld;                           // [TP] running log-det
+    int o_scl;                          // [FAB_NWARPS][TP] per-warp partial sums of the scales
     int o_const;                        // loc[DP], log_scale[DP], 1/scale[DP], logs[K]
     int o_state;                        // kernel-specific state area
     int total_floats;
 };
 
+__host__ __device__ __forceinline__ int fab_round8(int v) { return (v + 7) & ~7; }
+__host__ __device__ __forceinline__ int fab_round16(int v) { return (v + 15) & ~15; }
+
+// k-split plan of the narrow GEMMs (mma_gemm.cuh: mma_gemm_ksplit): NT n-tiles are spread over
+// NGR warp groups (<= 4 tiles per warp and pass), the remaining factor of the 8 warps splits K.
+__host__ __device__ inline void fab_ksplit_plan(int NT, int& NGR, int& KS) {
+    const int need = (NT + 3) / 4;
+    NGR = 1;
+    while (NGR < need && NGR < 8) NGR <<= 1;
+    KS = 8 / NGR;
+}
+
 // state_floats: extra per-CTA floats the calling kernel wants after the evaluation buffers.
-__host__ inline TileLayout make_tile_layout(const fab_flow_desc& f, int T, bool with_grad,
+__host__ inline TileLayout make_tile_layout(const fab_flow_desc& f, int T, int TP, bool with_grad,
                                             int state_floats) {
     TileLayout L{};
-    L.T = T; L.TP = fab_round4(T); L.d = f.dim; L.DP = fab_round4(f.dim);
-    const int TP = L.TP;
-    L.d1 = f.d1; L.d2 = f.d2; L.D1P = fab_round4(f.d1 > 0 ? f.d1 : 1);
-    L.P2 = fab_round4(2 * f.d2 > 0 ? 2 * f.d2 : 1);
-    L.WP = f.width_pad > 0 ? f.width_pad : 4;
-    L.MW = 4 * ((TP * L.WP / 4 + 31) / 32);
+    L.T = T; L.TP = TP; L.S = TP == 16 ? 24 : 8; L.RS = TP == 16 ? 20 : 12;
+    L.d = f.dim; L.DP = fab_round4(f.dim);
+    L.d1 = f.d1; L.d2 = f.d2;
+    L.D8 = fab_round8(f.dim); L.D16 = fab_round16(f.dim);
+    L.W8 = f.width_pad; L.W16 = f.width_kpad;
+    L.P8 = fab_round8(2 * f.d2); L.P16 = fab_round16(2 * f.d2);
+    L.D1K = fab_round16(f.d1);
+    L.NTH = L.W8 / 8;
+    L.MW = L.NTH * (TP == 16 ? 4 : 2);
     L.K = f.n_layers;
-    // reduction buffer: large enough for the k-splits that let each wide GEMM (N >= WP) occupy all
-    // FAB_NT threads (same arithmetic as gemm_plan in tile_gemm.cuh); rows are padded by 4 floats.
-    auto need = [&](int NP, int K4) {
-        int ks = FAB_NT / (NP / FAB_TN > 0 ? NP / FAB_TN : 1);
-        if (ks < 1) ks = 1;
-        if (ks > K4) ks = K4;
-        if (ks > 8) ks = 8;
-        return ks * T * (NP + 4);
+    auto need = [&](int N8) {
+        int NGR, KS; fab_ksplit_plan(N8 / 8, NGR, KS);
+        return KS * N8 * L.RS;
     };
-    L.red_floats = need(L.DP + L.WP, L.DP / 4 + 1);
-    if (need(L.WP, L.WP / 4 + 1) > L.red_floats) L.red_floats = need(L.WP, L.WP / 4 + 1);
-    if (need(L.WP, L.P2 / 4) > L.red_floats) L.red_floats = need(L.WP, L.P2 / 4);
-    if (need(L.DP, (L.WP + L.DP) / 4) > L.red_floats) L.red_floats = need(L.DP, (L.WP + L.DP) / 4);
+    L.red_floats = need(L.P8) > need(L.D8) ? need(L.P8) : need(L.D8);
+    const int S = L.S;
     int o = 0;
     auto take = [&](int n) { int r = o; o += fab_round4(n); return r; };
-    L.o_zs = take(TP * (L.DP + 4));
-    L.o_vs = take(TP * L.DP);
-    L.o_z1b = take(TP * (L.D1P + 4));
-    L.o_par = take(TP * L.P2);
-    L.o_h1 = take(TP * (L.WP + (L.DP > 4 ? L.DP : 4)));
-    L.o_h2 = take(TP * (L.WP + 4));
+    L.o_zs0 = take(L.D16 * S);
+    L.o_zs1 = take(L.D16 * S);
+    L.o_gs = take(L.D16 * S);
+    L.o_par = take(L.P16 * S);
+    L.o_h1 = take((L.W16 + L.D16) * S);
+    L.o_h2 = take((L.W16 > 0 ? L.W16 : 16) * S);
     L.o_red = take(L.red_floats);
-    int KS = with_grad ? L.K : 0;
-    L.o_sy2 = take(KS * T * L.d2);
-    L.o_ses = take(KS * T * L.d2);
-    L.o_m1 = take(KS * L.MW);
-    L.o_m2 = take(KS * L.MW);
-    L.o_ld = take(T);
-    L.o_scl = take(T * L.d2);
+    const int KSV = with_grad ? L.K : 0;
+    L.o_sy2 = take(KSV * L.d2 * TP);
+    L.o_ses = take(KSV * L.d2 * TP);
+    L.o_m1 = take(KSV * L.MW);
+    L.o_m2 = take(KSV * L.MW);
+    L.o_ld = take(TP);
+    L.o_scl = take(FAB_NWARPS * TP);
     L.o_const = take(3 * L.DP + L.K);
     L.o_state = take(state_floats);
     L.total_floats = o;

@@ -39,34 +39,26 @@ bool flow_ok(const fab_flow_desc* f) {
            (f->n_layers == 0 || f->width >= 1);
 }
 
-// Pick the particles-per-CTA variant: minimise (waves x T) = time of the FFMA-bound tile loop,
-// among the variants whose shared-memory layout fits; ties go to the larger tile (less L2 traffic).
+// Pick the particles per CTA (T) and the slot count of the MMA tile (TP = 8 or 16).  An MMA costs
+// the same for 1 or 16 live slots and the chain is sequential per particle, so the fastest split
+// spreads the batch over all SMs: T = ceil(n / n_SM) up to the 16 slots, then whole waves of 16.
+// Very wide flows whose TP = 16 layout does not fit shared memory fall back to 8 slots.
 template <typename StateFn>
 int pick_tile(const fab_flow_desc& f, long long n, bool with_grad, StateFn state_floats,
               TileLayout* out) {
-    const int cands[4] = {16, 14, 8, 4};
     static const int forced = getenv("FAB_FORCE_TILE") ? atoi(getenv("FAB_FORCE_TILE")) : 0;
-    long long best_cost = -1; int best = 0;
-    for (int c = 0; c < 4; ++c) {
-        const int T = cands[c];
-        if (forced && T != forced) continue;
-        TileLayout L = make_tile_layout(f, T, with_grad, state_floats(T, fab_round4(f.dim)));
-        const long long bytes = (long long)L.total_floats * 4;
-        if (bytes > kMaxSmemBytes) continue;
-        // CTAs that fit an SM together (shared memory: 228 KB per SM, 1 KB reserved per CTA;
-        // registers: FAB_MIN_CTAS in __launch_bounds__) overlap each other's serial phases
-        long long per_sm = (228 * 1024) / (bytes + 1024);
-        if (per_sm > FAB_MIN_CTAS) per_sm = FAB_MIN_CTAS;
-        if (per_sm < 1) per_sm = 1;
-        const long long ctas = (n + T - 1) / T;
-        const long long slots = (long long)sm_count() * per_sm;
-        const long long waves = (ctas + slots - 1) / slots;
-        // time ~ particles an SM has to carry one after the other
-        const long long on_sm = ctas < slots ? (ctas + sm_count() - 1) / sm_count() : per_sm;
-        const long long cost = waves * on_sm * T;
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = T; *out = L; }
+    long long T = (n + sm_count() - 1) / sm_count();
+    if (T > 16) T = 16;
+    if (T < 1) T = 1;
+    if (forced >= 1 && forced <= 16) T = forced;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int TP = T <= 8 ? 8 : 16;
+        TileLayout L = make_tile_layout(f, (int)T, TP, with_grad, state_floats((int)T, fab_round4(f.dim)));
+        if ((long long)L.total_floats * 4 <= kMaxSmemBytes) { *out = L; return (int)T; }
+        if (T <= 8) break;
+        T = 8;
     }
-    return best;
+    return 0;
 }
 
 template <typename K>
@@ -77,14 +69,12 @@ int set_smem(K kernel, const TileLayout& L) {
     return FAB_OK;
 }
 
-inline int sample_state(int T, int) { return fab_round4(T); }
+inline int sample_state(int, int) { return 16; }
 
-#define DISPATCH_T(T, ...)                       \
-    switch (T) {                                 \
-        case 16: { constexpr int TT = 16; __VA_ARGS__; } break; \
-        case 14: { constexpr int TT = 14; __VA_ARGS__; } break; \
-        case 8:  { constexpr int TT = 8;  __VA_ARGS__; } break; \
-        case 4:  { constexpr int TT = 4;  __VA_ARGS__; } break; \
+#define DISPATCH_TP(L, ...)                                      \
+    switch ((L).TP) {                                            \
+        case 16: { constexpr int TT = 16; __VA_ARGS__; } break;  \
+        case 8:  { constexpr int TT = 8;  __VA_ARGS__; } break;  \
         default: return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow"); \
     }
 
@@ -103,34 +93,41 @@ int64_t fab_flow_desc_init(fab_flow_desc* d, int32_t dim, int32_t width, int32_t
     d->d1 = (int32_t)((double)dim / 2 + 0.5);      // make_normflow_model.py:21
     d->d2 = dim - d->d1;
     d->width = n_layers > 0 ? width : 0;
-    d->width_pad = n_layers > 0 ? fab_round4(width) : 0;
+    d->width_pad = n_layers > 0 ? fab_round8(width) : 0;
+    d->width_kpad = n_layers > 0 ? fab_round16(width) : 0;
     d->n_layers = n_layers;
-    const int64_t DP = fab_round4(dim), D1P = fab_round4(d->d1), P2 = fab_round4(2 * d->d2),
-                  WP = d->width_pad;
+    const int64_t DP = fab_round4(dim), D8 = fab_round8(dim), D16 = fab_round16(dim),
+                  D1K = fab_round16(d->d1), P8 = fab_round8(2 * d->d2), P16 = fab_round16(2 * d->d2),
+                  W8 = d->width_pad, W16 = d->width_kpad;
     int64_t o = 0;
     d->off_base_loc = o; o += DP;
     d->off_base_log_scale = o; o += DP;
     d->off_layers = o;
     int64_t l = 0;
-    auto packed = [](int64_t K, int64_t NP) { return ((K + 3) / 4) * NP * 4; };
-    d->o_mw1 = l;     l += packed(DP + 4, DP + WP);
-    d->o_w2 = l;      l += packed(WP + 4, WP);
-    d->o_w3 = l;      l += packed(WP + 4, P2);
-    d->o_w3t = l;     l += packed(P2, WP);
-    d->o_w2t = l;     l += packed(WP, WP);
-    d->o_w1mt = l;    l += packed(WP + DP, DP);
-    d->o_w1 = l;      l += packed(D1P + 4, WP);
-    d->o_mix_inv = l; l += packed(DP, DP);
+    auto frag = [](int64_t K16, int64_t N8) { return (K16 / 16) * (N8 / 8) * 128; };
+    d->o_mw1 = l;     l += frag(D16, D8 + W8);
+    d->o_w2 = l;      l += frag(W16, W8);
+    d->o_w3 = l;      l += frag(W16, P8);
+    d->o_w3t = l;     l += frag(P16, W8);
+    d->o_w2t = l;     l += frag(W16, W8);
+    d->o_w1mt = l;    l += frag(W16 + D16, D8);
+    d->o_w1 = l;      l += frag(D1K, W8);
+    d->o_mix_inv = l; l += frag(D16, D8);
+    d->o_b1 = l;      l += D8 + W8;
+    d->o_b2 = l;      l += W8;
+    d->o_b3 = l;      l += P8;
     d->o_logs = l;    l += 4;
     d->layer_stride = l;
-    d->total_floats = o + (int64_t)n_layers * l;
+    d->total_floats = o + (int64_t)n_layers * l + 512;     // tail pad: L1 prefetches may run past the end
     return d->total_floats;
 }
 
 int fab_tile_particles(const fab_flow_desc* flow, int64_t n) {
     if (!flow_ok(flow) || n <= 0) return fail(FAB_E_INVALID, "fab_tile_particles: bad arguments");
     TileLayout L;
-    return pick_tile(*flow, n, true, hmc_state_floats, &L);
+    const int T = pick_tile(*flow, n, true, hmc_state_floats, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
+    return T;
 }
 
 int fab_flow_sample_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_eps,
@@ -140,8 +137,9 @@ int fab_flow_sample_f32(const fab_flow_desc* flow, const float* d_blob, const fl
     if (n == 0) return FAB_OK;
     TileLayout L;
     const int T = pick_tile(*flow, n, false, sample_state, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
     const unsigned grid = (unsigned)((n + T - 1) / T);
-    DISPATCH_T(T, {
+    DISPATCH_TP(L, {
         if (int e = set_smem(k_flow_sample<TT>, L)) return e;
         k_flow_sample<TT><<<grid, FAB_NT, L.total_floats * 4, (cudaStream_t)stream>>>(
             L, *flow, d_blob, d_eps, d_x, d_log_q, (long long)n);
@@ -158,10 +156,11 @@ int fab_flow_logprob_grad_f32(const fab_flow_desc* flow, const float* d_blob, co
     TileLayout L;
     const bool grad = d_grad != nullptr;
     const int T = pick_tile(*flow, n, grad, sample_state, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
     const unsigned grid = (unsigned)((n + T - 1) / T);
     const size_t sm = (size_t)L.total_floats * 4;
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(T, {
+    DISPATCH_TP(L, {
         if (grad) {
             if (int e = set_smem(k_flow_logprob<TT, true>, L)) return e;
             k_flow_logprob<TT, true><<<grid, FAB_NT, sm, s>>>(L, *flow, d_blob, d_x, d_log_q, d_grad,
@@ -207,10 +206,11 @@ int fab_ais_init_f32(const fab_flow_desc* flow, const float* d_blob, const fab_t
     if (n == 0) return FAB_OK;
     TileLayout L;
     const int T = pick_tile(*flow, n, with_grad != 0, init_state_floats, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
     const unsigned grid = (unsigned)((n + T - 1) / T);
     const size_t sm = (size_t)L.total_floats * 4;
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(T, {
+    DISPATCH_TP(L, {
         if (with_grad) {
             if (int e = set_smem(k_ais_init<TT, true>, L)) return e;
             k_ais_init<TT, true><<<grid, FAB_NT, sm, s>>>(L, *flow, d_blob, *target, d_eps, g1, out,
@@ -228,7 +228,7 @@ int fab_ais_init_f32(const fab_flow_desc* flow, const float* d_blob, const fab_t
 int64_t fab_hmc_workspace_bytes(const fab_flow_desc* flow, int64_t n) {
     (void)flow;
     if (n < 0) return FAB_E_INVALID;
-    return ((n + 3) / 4) * 2 * (int64_t)sizeof(float) + 64;   // smallest tile (4) => most CTAs
+    return n * 2 * (int64_t)sizeof(float) + 64;               // smallest tile (1) => most CTAs
 }
 
 int fab_hmc_step_f32(const fab_flow_desc* flow, const float* d_blob, const fab_target_desc* target,
@@ -252,9 +252,10 @@ int fab_hmc_step_f32(const fab_flow_desc* flow, const float* d_blob, const fab_t
     if (n == 0) return FAB_OK;
     TileLayout L;
     const int T = pick_tile(*flow, n, true, hmc_state_floats, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
     const unsigned grid = (unsigned)((n + T - 1) / T);
     const size_t sm = (size_t)L.total_floats * 4;
-    DISPATCH_T(T, {
+    DISPATCH_TP(L, {
         if (int e = set_smem(k_hmc_step<TT>, L)) return e;
         k_hmc_step<TT><<<grid, FAB_NT, sm, (cudaStream_t)stream>>>(
             L, *flow, d_blob, *target, st, a, cur, prop_in, prop_out, d_log_w, d_mom_noise,
@@ -275,7 +276,7 @@ int fab_hmc_finish_f32(fab_hmc_state st, fab_hmc_args a, const float* d_stats, v
 int64_t fab_metropolis_workspace_bytes(const fab_flow_desc* flow, int64_t n, int32_t n_updates) {
     (void)flow; (void)n_updates;
     if (n < 0) return FAB_E_INVALID;
-    return ((n + 3) / 4) * FAB_MAX_UPDATES * (int64_t)sizeof(float) + 64;
+    return n * FAB_MAX_UPDATES * (int64_t)sizeof(float) + 64;
 }
 
 int fab_metropolis_transition_f32(const fab_flow_desc* flow, const float* d_blob,
@@ -292,9 +293,10 @@ int fab_metropolis_transition_f32(const fab_flow_desc* flow, const float* d_blob
     if (n == 0) return FAB_OK;
     TileLayout L;
     const int T = pick_tile(*flow, n, false, metro_state_floats, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
     const unsigned grid = (unsigned)((n + T - 1) / T);
     const size_t sm = (size_t)L.total_floats * 4;
-    DISPATCH_T(T, {
+    DISPATCH_TP(L, {
         if (int e = set_smem(k_metropolis<TT>, L)) return e;
         k_metropolis<TT><<<grid, FAB_NT, sm, (cudaStream_t)stream>>>(
             L, *flow, d_blob, *target, a, d_noise_scalings, cur, d_log_w, d_prop_noise, d_unif,
@@ -398,5 +400,18 @@ int fab_gather_rows_f32(const float* d_src, float* d_dst, const int64_t* d_anc, 
     CK_LAUNCH("k_gather_rows");
     return FAB_OK;
 }
+
+#ifdef FAB_PROF
+// experiment builds only: read (and optionally clear) the per-phase cycle counters of CTA 0
+int fab_debug_prof(unsigned long long* out32, int reset) {
+    if (cudaMemcpyFromSymbol(out32, g_fab_prof, sizeof(unsigned long long) * 32) != cudaSuccess)
+        return FAB_E_CUDA;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(g_fab_prof, z, sizeof(z)) != cudaSuccess) return FAB_E_CUDA;
+    }
+    return FAB_OK;
+}
+#endif
 
 }  // extern "C"

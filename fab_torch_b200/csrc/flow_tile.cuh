@@ -1,4 +1,4 @@
-// RealNVP evaluation for the T particles of one CTA, entirely in shared memory.
+// RealNVP evaluation for the particles of one CTA, entirely in shared memory.
 //
 //   flow_inverse  : x -> z, log q(x)             normflows NormalizingFlow.log_prob  (K3)
 //   flow_backward : d log q / d x                analytic reverse sweep, replaces
@@ -11,23 +11,36 @@
 //   inverse,  layer k:  v = u @ Wmix; (shift,scale) = MLP(v1);  y2 = (v2-shift)*exp(-scale);
 //                       u' = [v1,y2];           log q += sum(log_S) - sum(scale)
 // Per layer and direction this is three GEMMs (include/fab_b200.h: o_mw1/o_w2/o_w3 and
-// o_w3t/o_w2t/o_w1mt): the mixing matrix is merged into the neighbouring MLP GEMM and biases ride
-// along as an extra K row against a constant-one activation row.
+// o_w3t/o_w2t/o_w1mt): the mixing matrix is merged into the neighbouring MLP GEMM.  The two wide
+// GEMMs of a direction finish in their accumulator fragments (bias = accumulator init, ReLU +
+// mask ballots / mask select in registers, results stored as the next GEMM's operand); the narrow
+// third GEMM splits K over the warps and its partials meet in the coupling step.
 //
-// zs, vs, z1b, par, h1, h2 are GEMM operands in the k-major / particle-fastest layout
-// (tile_gemm.cuh): element (p, n) of any of them sits at float index kidx<T>(p, n) = n*TP + p.
+// zs0/zs1, gs, par, h1, h2 are MMA operands in the k-major layout of mma_gemm.cuh: element
+// (slot p, row n) of any of them sits at float index n*S + p.
 #pragma once
-#include "tile_gemm.cuh"
+#include "mma_gemm.cuh"
 
 struct TileBufs {
-    float *zs, *vs, *z1b, *par, *h1, *h2, *red, *sy2, *ses, *ld, *scl;
+    float *gs, *par, *h1, *h2, *red, *sy2, *ses, *ld, *scl;
     float *loc, *lsc, *inv, *logs;          // staged constants
     uint32_t *m1, *m2;
 };
 
-__device__ __forceinline__ TileBufs tile_bufs(const TileLayout& L, float* smem) {
+// The one dynamic shared-memory array of every tile kernel.  Each device function re-derives its
+// buffer pointers from it (instead of receiving a struct of generic pointers) so that the
+// compiler knows the address space and emits LDS/STS, and nothing is parked in local memory.
+extern __shared__ __align__(16) float fab_smem[];
+
+// the two ping-pong operand buffers of the running latent (offset select keeps the address space)
+__device__ __forceinline__ float* zsel(const TileLayout& L, int which) {
+    return fab_smem + (which ? L.o_zs1 : L.o_zs0);
+}
+
+__device__ __forceinline__ TileBufs tile_bufs(const TileLayout& L) {
+    float* const smem = fab_smem;
     TileBufs b;
-    b.zs = smem + L.o_zs;   b.vs = smem + L.o_vs;   b.z1b = smem + L.o_z1b;
+    b.gs = smem + L.o_gs;
     b.par = smem + L.o_par; b.h1 = smem + L.o_h1;   b.h2 = smem + L.o_h2;
     b.red = smem + L.o_red; b.sy2 = smem + L.o_sy2; b.ses = smem + L.o_ses;
     b.ld = smem + L.o_ld;   b.scl = smem + L.o_scl;
@@ -37,28 +50,14 @@ __device__ __forceinline__ TileBufs tile_bufs(const TileLayout& L, float* smem) 
     return b;
 }
 
-// rows [row, row+4) of an operand buffer := (1,0,0,0) pattern: the constant activation that
-// multiplies the bias row of an operand
-template <int T>
-__device__ __forceinline__ void set_one_rows(float* buf, int row) {
-    constexpr int TP = TileDims<T>::TP;
-    for (int i = threadIdx.x; i < 4 * TP; i += FAB_NT) buf[(size_t)row * TP + i] = i < TP ? 1.f : 0.f;
-}
-
-// Once per kernel: zero the operand buffers (pad rows/columns must stay exactly 0 because the
-// packed weights multiply them by 0 and 0*inf would poison a row), set the bias rows, and stage
-// the small per-flow constants (base loc / log_scale, per-layer sum(log_S)) in shared memory so
-// that no serial code path waits on an L2 round trip.
-template <int T>
-__device__ __forceinline__ void tile_init(const TileLayout& L, const TileBufs& b,
-                                          const fab_flow_desc& f, const float* __restrict__ blob) {
-    constexpr int TP = TileDims<T>::TP;
-    for (int i = threadIdx.x; i < TP * (L.DP + 4); i += FAB_NT) b.zs[i] = 0.f;
-    for (int i = threadIdx.x; i < TP * L.DP; i += FAB_NT) b.vs[i] = 0.f;
-    for (int i = threadIdx.x; i < TP * (L.D1P + 4); i += FAB_NT) b.z1b[i] = 0.f;
-    for (int i = threadIdx.x; i < TP * L.P2; i += FAB_NT) b.par[i] = 0.f;
-    for (int i = threadIdx.x; i < TP * (L.WP + (L.DP > 4 ? L.DP : 4)); i += FAB_NT) b.h1[i] = 0.f;
-    for (int i = threadIdx.x; i < TP * (L.WP + 4); i += FAB_NT) b.h2[i] = 0.f;
+// Once per kernel: zero the operand buffers (pad rows/slots must stay finite because the MMAs
+// multiply them by zero weights / feed them to unused accumulator rows) and stage the small
+// per-flow constants (base loc / log_scale, per-layer sum(log_S)) in shared memory so that no
+// serial code path waits on an L2 round trip.
+__device__ __forceinline__ void tile_init(const TileLayout& L, const fab_flow_desc& f, const float* __restrict__ blob) {
+    const TileBufs b = tile_bufs(L);
+    float* const smem = fab_smem;
+    for (int i = threadIdx.x; i < L.o_red; i += FAB_NT) smem[i] = 0.f;     // zs0..h2 are contiguous
     for (int j = threadIdx.x; j < L.DP; j += FAB_NT) {
         const float loc = j < L.d ? __ldg(blob + f.off_base_loc + j) : 0.f;
         const float ls = j < L.d ? __ldg(blob + f.off_base_log_scale + j) : 0.f;
@@ -67,296 +66,314 @@ __device__ __forceinline__ void tile_init(const TileLayout& L, const TileBufs& b
     for (int k = threadIdx.x; k < L.K; k += FAB_NT)
         b.logs[k] = __ldg(blob + f.off_layers + (size_t)k * f.layer_stride + f.o_logs);
     __syncthreads();
-    set_one_rows<T>(b.zs, L.DP);
-    set_one_rows<T>(b.z1b, L.D1P);
-    set_one_rows<T>(b.h1, L.WP);
-    set_one_rows<T>(b.h2, L.WP);
-    __syncthreads();
 }
 
-// hidden-layer epilogue; one quad (4 consecutive particles of one column) per lane and step:
-// FWD: h = relu(sum)  (bias already inside the GEMM), ReLU masks = 4 ballots per 32 quads;
-// BWD: h = mask ? sum : 0.   `col0` = first column of this block inside the GEMM output.
-template <int T, bool FWD, bool SAVE>
-__device__ __forceinline__ void hidden_epilogue(const TileLayout& L, const float* red, int KS,
-                                                int NP, int col0, float* h, uint32_t* mask) {
-    constexpr int TP = TileDims<T>::TP;
-    // work item q = (column quad n4, particle p), particle fastest: the KS partial rows are read
-    // with one LDS.128 each (conflict-free: rows are NP+4 floats apart) and the four results go
-    // to h[4*n4+i][p] (consecutive lanes -> consecutive floats).
-    const int lane = threadIdx.x & 31;
-    const int nq = (L.WP >> 2) * T;
-    const int NPs = NP + 4;
-    const int stride = T * NPs;
-    for (int q0 = (threadIdx.x & ~31); q0 < nq; q0 += FAB_NT) {
-        const int q = q0 + lane;
-        const bool in = q < nq;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        int n4 = 0, p = 0;
-        if (in) {
-            n4 = q / T;
-            p = q - n4 * T;
-            const float* r = red + p * NPs + col0 + (n4 << 2);
-            v = *reinterpret_cast<const float4*>(r);
-#pragma unroll 4
-            for (int ks = 1; ks < KS; ++ks) {
-                r += stride;
-                const float4 u = *reinterpret_cast<const float4*>(r);
-                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-            }
-        }
-        uint32_t* mw = mask + ((q0 >> 5) << 2);
-        float* hp = h + (size_t)(n4 << 2) * TP + p;
-        if (FWD) {
-            const bool px = in && v.x > 0.f, py = in && v.y > 0.f, pz = in && v.z > 0.f,
-                       pw = in && v.w > 0.f;
-            if (SAVE) {
-                const uint32_t bx = __ballot_sync(FAB_FULL, px), by = __ballot_sync(FAB_FULL, py),
-                               bz = __ballot_sync(FAB_FULL, pz), bw = __ballot_sync(FAB_FULL, pw);
-                if (lane == 0) *reinterpret_cast<uint4*>(mw) = make_uint4(bx, by, bz, bw);
-            }
-            if (in) {
-                hp[0] = px ? v.x : 0.f; hp[TP] = py ? v.y : 0.f;
-                hp[2 * TP] = pz ? v.z : 0.f; hp[3 * TP] = pw ? v.w : 0.f;
-            }
+// ---- accumulator-fragment epilogues of the wide GEMMs ------------------------------------------
+// store fragment (tile column block n0 = 8*tile) as rows n0+2t, n0+2t+1 of an operand buffer
+template <int TP>
+__device__ __forceinline__ void frag_store(float* dst, int n0, int g, int t, float c0, float c1,
+                                           float c2, float c3) {
+    constexpr int S = ActL<TP>::S;
+    float* r = dst + (size_t)(n0 + 2 * t) * S + g;
+    r[0] = c0; r[S] = c1;
+    if (TP == 16) { r[8] = c2; r[S + 8] = c3; }
+}
+
+// h = relu(c) -> dst tile `ht`; with SAVE the ReLU masks are kept as one ballot per fragment
+// register (word layout [ht][TP==16 ? 4 : 2])
+template <int TP, bool SAVE>
+__device__ __forceinline__ void hidden_fwd(float* dst, uint32_t* mask, int ht, int g, int t,
+                                           const float (&c)[4]) {
+    const bool p0 = c[0] > 0.f, p1 = c[1] > 0.f, p2 = c[2] > 0.f, p3 = c[3] > 0.f;
+    if (SAVE) {
+        const uint32_t b0 = __ballot_sync(FAB_FULL, p0), b1 = __ballot_sync(FAB_FULL, p1);
+        if (TP == 16) {
+            const uint32_t b2 = __ballot_sync(FAB_FULL, p2), b3 = __ballot_sync(FAB_FULL, p3);
+            if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint4*>(mask + 4 * ht) = make_uint4(b0, b1, b2, b3);
         } else {
-            const uint4 bits = *reinterpret_cast<const uint4*>(mw);
-            if (in) {
-                hp[0] = (bits.x >> lane) & 1u ? v.x : 0.f; hp[TP] = (bits.y >> lane) & 1u ? v.y : 0.f;
-                hp[2 * TP] = (bits.z >> lane) & 1u ? v.z : 0.f; hp[3 * TP] = (bits.w >> lane) & 1u ? v.w : 0.f;
-            }
+            if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint2*>(mask + 2 * ht) = make_uint2(b0, b1);
         }
     }
+    frag_store<TP>(dst, 8 * ht, g, t, p0 ? c[0] : 0.f, p1 ? c[1] : 0.f, p2 ? c[2] : 0.f,
+                   p3 ? c[3] : 0.f);
 }
 
-// MLP stages 2 and 3 (h1 -> h2 -> [shift|scale] partial sums in red, NP = P2); returns KS.
-// `next_*` describe the GEMM that follows the coupling step (prefetched behind the last barrier).
-template <int T, bool SAVE>
-__device__ __forceinline__ int mlp_tail(const TileLayout& L, const TileBufs& b,
-                                        const float* __restrict__ lay, const fab_flow_desc& f,
-                                        int k, const float* next_wp, int next_K4, int next_NP) {
-    int KS = tile_gemm<T>(b.h1, L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
-                          b.red, L.red_floats);
-    tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w3), L.P2,
-                          L.red_floats);
-    __syncthreads();
-    hidden_epilogue<T, true, SAVE>(L, b.red, KS, L.WP, 0, b.h2,
-                                   SAVE ? b.m2 + (size_t)k * L.MW : nullptr);
-    __syncthreads();
-    KS = tile_gemm<T>(b.h2, L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w3), L.P2,
-                      b.red, L.red_floats);
-    if (next_wp)
-        tile_gemm_prefetch<T>(next_K4, reinterpret_cast<const float4*>(next_wp), next_NP,
-                              L.red_floats);
-    __syncthreads();
-    return KS;
-}
-
-// per-particle  ld[p] += add - sum_j scl[p][j]
-template <int T>
-__device__ __forceinline__ void logdet_accumulate(const TileLayout& L, const TileBufs& b, float add) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int p = warp; p < T; p += FAB_NWARPS) {
-        float s = 0.f;
-        for (int j = lane; j < L.d2; j += 32) s += b.scl[p * L.d2 + j];
-        s = warp_sum(s);
-        if (lane == 0) b.ld[p] += add - s;
+// gh = mask ? c : 0 -> dst tile `ht`
+template <int TP>
+__device__ __forceinline__ void hidden_bwd(float* dst, const uint32_t* mask, int ht, int g, int t,
+                                           const float (&c)[4]) {
+    const int lane = threadIdx.x & 31;
+    if (TP == 16) {
+        const uint4 m = *reinterpret_cast<const uint4*>(mask + 4 * ht);
+        frag_store<TP>(dst, 8 * ht, g, t, (m.x >> lane) & 1u ? c[0] : 0.f, (m.y >> lane) & 1u ? c[1] : 0.f,
+                       (m.z >> lane) & 1u ? c[2] : 0.f, (m.w >> lane) & 1u ? c[3] : 0.f);
+    } else {
+        const uint2 m = *reinterpret_cast<const uint2*>(mask + 2 * ht);
+        frag_store<TP>(dst, 8 * ht, g, t, (m.x >> lane) & 1u ? c[0] : 0.f, (m.y >> lane) & 1u ? c[1] : 0.f,
+                       0.f, 0.f);
     }
 }
 
-// x in b.zs  ->  z in b.zs, log q in lq_out[p] (shared).  With SAVE the per-layer
-// (y2, exp(-scale), ReLU masks) needed by flow_backward are kept and b.vs is set to
-// d log N(z) / dz.
-template <int T, bool SAVE>
-__device__ void flow_inverse(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
-                             const float* __restrict__ blob, float* lq_out) {
-    constexpr int TP = TileDims<T>::TP;
-    for (int p = threadIdx.x; p < T; p += FAB_NT) b.ld[p] = 0.f;
-    const int NP1 = L.DP + L.WP;
+// MLP stages 2 and 3 (h1 -> h2 -> [shift|scale] partials in red); returns the partial count KSe.
+// `next_wf` describes the GEMM that follows the coupling step (prefetched behind the last barrier).
+template <int TP, bool SAVE>
+__device__ __forceinline__ int mlp_tail(const TileLayout& L, const float* __restrict__ lay, const fab_flow_desc& f,
+                                        int k, const float* next_wf, int next_NT, bool next_ksplit) {
+    const TileBufs b = tile_bufs(L);
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint32_t* m2 = SAVE ? b.m2 + (size_t)k * L.MW : nullptr;
+    float* h2 = b.h2;
+    mma_gemm_wide<TP>(b.h1, L.W16 / 16, reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH,
+                      lay + f.o_b2, [&](int nt, const float (&c)[4]) {
+                          hidden_fwd<TP, SAVE>(h2, m2, nt, g, t, c);
+                      });
+    mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w3), L.P8 / 8, true);
+    __syncthreads();
+    prof_mark(5);
+    const int KSe = mma_gemm_ksplit<TP>(b.h2, L.W16 / 16, reinterpret_cast<const float4*>(lay + f.o_w3),
+                                        L.P8 / 8, b.red);
+    if (next_wf) mma_prefetch(reinterpret_cast<const float4*>(next_wf), next_NT, next_ksplit);
+    __syncthreads();
+    prof_mark(7);
+    return KSe;
+}
+
+// ld[p] += add - sum_w scl[w][p]   (threads < TP; scl holds the per-warp partial scale sums)
+template <int TP>
+__device__ __forceinline__ void logdet_accumulate(const TileBufs& b, float add) {
+    if (threadIdx.x < TP) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < FAB_NWARPS; ++w) s += b.scl[w * TP + threadIdx.x];
+        b.ld[threadIdx.x] += add - s;
+    }
+}
+
+// sum a per-thread value over the threads that share slot p = tid % TP inside a warp and deposit
+// it in scl[warp][p]
+template <int TP>
+__device__ __forceinline__ void slot_partial(const TileBufs& b, float v) {
+    v += __shfl_xor_sync(FAB_FULL, v, 16);
+    if (TP == 8) v += __shfl_xor_sync(FAB_FULL, v, 8);
+    const int lane = threadIdx.x & 31;
+    if (lane < TP) b.scl[(threadIdx.x >> 5) * TP + lane] = v;
+}
+
+// x in zsel(L, cur) -> z in zsel(L, cur') (cur' returned), log q in lq_out[p] (shared, p < TP).  With
+// SAVE the per-layer (y2, exp(-scale), ReLU masks) needed by flow_backward are kept and b.gs is
+// set to d log N(z) / dz.
+template <int TP, bool SAVE>
+__device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
+                            const float* __restrict__ blob, int cur, float* lq_out) {
+    const TileBufs b = tile_bufs(L);
+    constexpr int S = ActL<TP>::S;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    if (threadIdx.x < TP) b.ld[threadIdx.x] = 0.f;
+    const int NT1 = L.D8 / 8 + L.NTH, NTV = L.D8 / 8;
     for (int k = L.K - 1; k >= 0; --k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
-        // [v | h1pre] = [z | 1] @ [Wmix | Wmix[:, :d1] W1^T ; 0 | b1]
-        int KS = tile_gemm<T>(b.zs, L.DP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_mw1),
-                              NP1, b.red, L.red_floats);
-        tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
-                              L.red_floats);
+        // [v | h1pre] = z @ [Wmix | Wmix[:, :d1] W1^T] + [0 | b1]
+        float* zn = zsel(L, cur ^ 1);
+        float* h1 = b.h1;
+        uint32_t* m1 = SAVE ? b.m1 + (size_t)k * L.MW : nullptr;
+        mma_gemm_wide<TP>(zsel(L, cur), L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mw1), NT1,
+                          lay + f.o_b1, [&](int nt, const float (&c)[4]) {
+                              if (nt < NTV) frag_store<TP>(zn, 8 * nt, g, t, c[0], c[1], c[2], c[3]);
+                              else hidden_fwd<TP, SAVE>(h1, m1, nt - NTV, g, t, c);
+                          });
+        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false);
         __syncthreads();
-        for (int e = threadIdx.x; e < TP * L.d; e += FAB_NT) {
-            int p, n;
-            kdecode<T>(e, p, n);
-            if (p < T) {
-                const float v = red_sum<T>(b.red, KS, NP1, p, n);
-                b.vs[e] = v;
-                if (n < L.d1) b.zs[e] = v;
-            }
-        }
-        hidden_epilogue<T, true, SAVE>(L, b.red, KS, NP1, L.DP, b.h1,
-                                       SAVE ? b.m1 + (size_t)k * L.MW : nullptr);
-        if (SAVE) set_one_rows<T>(b.h1, L.WP);        // flow_backward parks [gv] in these rows
-        __syncthreads();
-        KS = mlp_tail<T, SAVE>(L, b, lay, f, k, k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr,
-                               L.DP / 4 + 1, NP1);
+        prof_mark(3);
+        const int KSe = mlp_tail<TP, SAVE>(L, lay, f, k,
+                                           k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr, NT1, false);
         // coupling inverse: y2 = (v2 - shift) * exp(-scale)
-        for (int i = threadIdx.x; i < T * L.d2; i += FAB_NT) {
-            const int j = i / T, p = i - j * T;
-            const float shift = red_sum<T>(b.red, KS, L.P2, p, j);
-            const float scale = red_sum<T>(b.red, KS, L.P2, p, L.d2 + j);
-            const float es = expf(-scale);
-            const int e = kidx<T>(p, L.d1 + j);
-            const float y2 = (b.vs[e] - shift) * es;
-            b.zs[e] = y2;
-            b.scl[p * L.d2 + j] = scale;
-            if (SAVE) {
-                b.sy2[((size_t)k * T + p) * L.d2 + j] = y2;
-                b.ses[((size_t)k * T + p) * L.d2 + j] = es;
+        {
+            const float* b3 = lay + f.o_b3;
+            float ssum = 0.f;
+            for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) {
+                const int j = e / TP, p = e - j * TP;
+                const float shift = red_sum<TP>(b.red, KSe, L.P8, p, j) + __ldg(b3 + j);
+                const float scale = red_sum<TP>(b.red, KSe, L.P8, p, L.d2 + j) + __ldg(b3 + L.d2 + j);
+                const float es = expf(-scale);
+                float* zp = zn + (size_t)(L.d1 + j) * S + p;
+                const float y2 = (*zp - shift) * es;
+                *zp = y2;
+                ssum += scale;
+                if (SAVE) {
+                    b.sy2[((size_t)k * L.d2 + j) * TP + p] = y2;
+                    b.ses[((size_t)k * L.d2 + j) * TP + p] = es;
+                }
             }
+            slot_partial<TP>(b, ssum);
         }
         __syncthreads();
-        logdet_accumulate<T>(L, b, b.logs[k]);
-        // (scl / ld are next touched after at least one more barrier)
+        logdet_accumulate<TP>(b, b.logs[k]);
+        prof_mark(8);
+        cur ^= 1;
+        // (scl / ld are next touched after at least two more barriers)
     }
     __syncthreads();
     // base Gaussian: log N(z; loc, exp(log_scale)) and its z-gradient
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int p = warp; p < T; p += FAB_NWARPS) {
-            float s = 0.f;
-            for (int j = lane; j < L.d; j += 32) {
-                const float inv = b.inv[j];
-                const int e = kidx<T>(p, j);
-                const float u = (b.zs[e] - b.loc[j]) * inv;
-                s += b.lsc[j] + 0.5f * u * u;
-                if (SAVE) b.vs[e] = -u * inv;
-            }
-            s = warp_sum(s);
-            if (lane == 0)
-                lq_out[p] = b.ld[p] + (-0.5f * (float)L.d * 1.8378770664093453f - s);
+        const float* z = zsel(L, cur);
+        float s = 0.f;
+        for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
+            const int j = e / TP, p = e - j * TP;
+            const float inv = b.inv[j];
+            const float u = (z[(size_t)j * S + p] - b.loc[j]) * inv;
+            s += b.lsc[j] + 0.5f * u * u;
+            if (SAVE) b.gs[(size_t)j * S + p] = -u * inv;
+        }
+        slot_partial<TP>(b, s);
+        __syncthreads();
+        if (threadIdx.x < TP) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < FAB_NWARPS; ++w) tot += b.scl[w * TP + threadIdx.x];
+            lq_out[threadIdx.x] = b.ld[threadIdx.x] + (-0.5f * (float)L.d * 1.8378770664093453f - tot);
         }
     }
     __syncthreads();
+    prof_mark(9);
+    return cur;
 }
 
-// b.vs holds d log q / d z on entry (set by flow_inverse<SAVE=true>) and d log q / d x on exit.
-template <int T>
-__device__ void flow_backward(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
+// b.gs holds d log q / d z on entry (set by flow_inverse<SAVE=true>) and d log q / d x on exit.
+template <int TP>
+__device__ void flow_backward(const TileLayout& L, const fab_flow_desc& f,
                               const float* __restrict__ blob) {
-    constexpr int TP = TileDims<T>::TP;
-    float* gs = b.vs;
-    float* gv = b.h1 + (size_t)L.WP * TP;               // [gv] rows behind gh1
+    const TileBufs b = tile_bufs(L);
+    constexpr int S = ActL<TP>::S;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float* gs = b.gs;
+    float* gv = b.h1 + (size_t)L.W16 * S;               // [gv] rows behind gh1
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
         // coupling backward: gv2 = g2*es, gshift = -gv2, gscale = -g2*y2 - 1
-        for (int i = threadIdx.x; i < T * L.d2; i += FAB_NT) {
-            const int j = i / T, p = i - j * T;
-            const float es = b.ses[((size_t)k * T + p) * L.d2 + j];
-            const float y2 = b.sy2[((size_t)k * T + p) * L.d2 + j];
-            const int e = kidx<T>(p, L.d1 + j);
-            const float g2 = gs[e];
+        for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) {
+            const int j = e / TP, p = e - j * TP;
+            const float es = b.ses[((size_t)k * L.d2 + j) * TP + p];
+            const float y2 = b.sy2[((size_t)k * L.d2 + j) * TP + p];
+            const float g2 = gs[(size_t)(L.d1 + j) * S + p];
             const float gv2 = g2 * es;
-            b.par[kidx<T>(p, j)] = -gv2;
-            b.par[kidx<T>(p, L.d2 + j)] = -g2 * y2 - 1.0f;
-            gv[e] = gv2;
+            b.par[(size_t)j * S + p] = -gv2;
+            b.par[(size_t)(L.d2 + j) * S + p] = -g2 * y2 - 1.0f;
+            gv[(size_t)(L.d1 + j) * S + p] = gv2;
         }
-        for (int e = threadIdx.x; e < TP * L.DP; e += FAB_NT) {
-            int p, n;
-            kdecode<T>(e, p, n);
-            if (n < L.d1) gv[e] = p < T ? gs[e] : 0.f;
-            else if (n >= L.d) gv[e] = 0.f;
+        for (int e = threadIdx.x; e < L.d1 * TP; e += FAB_NT) {
+            const int j = e / TP, p = e - j * TP;
+            gv[(size_t)j * S + p] = gs[(size_t)j * S + p];
         }
         __syncthreads();
+        prof_mark(10);
         // gh2 = (gparam @ W3) * m2
-        int KS = tile_gemm<T>(b.par, L.P2 / 4, reinterpret_cast<const float4*>(lay + f.o_w3t), L.WP,
-                              b.red, L.red_floats);
-        tile_gemm_prefetch<T>(L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w2t), L.WP,
-                              L.red_floats);
+        {
+            float* h2 = b.h2;
+            const uint32_t* m2 = b.m2 + (size_t)k * L.MW;
+            mma_gemm_wide<TP>(b.par, L.P16 / 16, reinterpret_cast<const float4*>(lay + f.o_w3t), L.NTH,
+                              nullptr, [&](int nt, const float (&c)[4]) {
+                                  hidden_bwd<TP>(h2, m2, nt, g, t, c);
+                              });
+        }
+        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2t), L.NTH, false);
         __syncthreads();
-        hidden_epilogue<T, false, false>(L, b.red, KS, L.WP, 0, b.h2, b.m2 + (size_t)k * L.MW);
-        __syncthreads();
+        prof_mark(11);
         // gh1 = (gh2 @ W2) * m1
-        KS = tile_gemm<T>(b.h2, L.WP / 4, reinterpret_cast<const float4*>(lay + f.o_w2t), L.WP,
-                          b.red, L.red_floats);
-        tile_gemm_prefetch<T>((L.WP + L.DP) / 4, reinterpret_cast<const float4*>(lay + f.o_w1mt),
-                              L.DP, L.red_floats);
+        {
+            float* h1 = b.h1;
+            const uint32_t* m1 = b.m1 + (size_t)k * L.MW;
+            mma_gemm_wide<TP>(b.h2, L.W16 / 16, reinterpret_cast<const float4*>(lay + f.o_w2t), L.NTH,
+                              nullptr, [&](int nt, const float (&c)[4]) {
+                                  hidden_bwd<TP>(h1, m1, nt, g, t, c);
+                              });
+        }
+        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, true);
         __syncthreads();
-        hidden_epilogue<T, false, false>(L, b.red, KS, L.WP, 0, b.h1, b.m1 + (size_t)k * L.MW);
-        __syncthreads();
+        prof_mark(13);
         // g_u = [gh1 | gv] @ [W1 Wmix[:, :d1]^T ; Wmix^T]
-        KS = tile_gemm<T>(b.h1, (L.WP + L.DP) / 4, reinterpret_cast<const float4*>(lay + f.o_w1mt),
-                          L.DP, b.red, L.red_floats);
+        const int KSe = mma_gemm_ksplit<TP>(b.h1, (L.W16 + L.D16) / 16,
+                                            reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, b.red);
         if (k + 1 < L.K)
-            tile_gemm_prefetch<T>(L.P2 / 4,
-                                  reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t),
-                                  L.WP, L.red_floats);
+            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t), L.NTH, false);
         __syncthreads();
-        for (int e = threadIdx.x; e < TP * L.d; e += FAB_NT) {
-            int p, n;
-            kdecode<T>(e, p, n);
-            if (p < T) gs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
+        prof_mark(15);
+        for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
+            const int j = e / TP, p = e - j * TP;
+            gs[(size_t)j * S + p] = red_sum<TP>(b.red, KSe, L.D8, p, j);
         }
         __syncthreads();
+        prof_mark(16);
     }
 }
 
-// eps in b.zs -> x in b.zs, forward-pass log q in lq_out[p].
-template <int T>
-__device__ void flow_sample(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
-                            const float* __restrict__ blob, float* lq_out) {
-    constexpr int TP = TileDims<T>::TP;
+// eps in zsel(L, cur) -> x in zsel(L, cur) (same buffer), forward-pass log q in lq_out[p].
+template <int TP>
+__device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
+                            const float* __restrict__ blob, int cur, float* lq_out) {
+    const TileBufs b = tile_bufs(L);
+    constexpr int S = ActL<TP>::S;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float* z = zsel(L, cur);
     {   // base: z = loc + exp(log_scale)*eps ; log p0 = -d/2 log 2pi - sum(log_scale + eps^2/2)
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int p = warp; p < T; p += FAB_NWARPS) {
-            float s = 0.f;
-            for (int j = lane; j < L.d; j += 32) {
-                const float ls = b.lsc[j];
-                const int e = kidx<T>(p, j);
-                const float ev = b.zs[e];
-                s += ls + 0.5f * ev * ev;
-                b.zs[e] = b.loc[j] + expf(ls) * ev;
-            }
-            s = warp_sum(s);
-            if (lane == 0) b.ld[p] = -0.5f * (float)L.d * 1.8378770664093453f - s;
+        float s = 0.f;
+        for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
+            const int j = e / TP, p = e - j * TP;
+            const float ls = b.lsc[j];
+            const float ev = z[(size_t)j * S + p];
+            s += ls + 0.5f * ev * ev;
+            z[(size_t)j * S + p] = b.loc[j] + expf(ls) * ev;
         }
+        slot_partial<TP>(b, s);
+        __syncthreads();
+        if (threadIdx.x < TP) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < FAB_NWARPS; ++w) tot += b.scl[w * TP + threadIdx.x];
+            b.ld[threadIdx.x] = -0.5f * (float)L.d * 1.8378770664093453f - tot;
+        }
+        __syncthreads();
     }
-    set_one_rows<T>(b.h1, L.WP);
-    __syncthreads();
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
-        for (int e = threadIdx.x; e < TP * L.d1; e += FAB_NT) b.z1b[e] = b.zs[e];
+        // h1 = relu(z1 @ W1^T + b1): rows >= d1 of the operand meet zero weight rows
+        {
+            float* h1 = b.h1;
+            mma_gemm_wide<TP>(z, L.D1K / 16, reinterpret_cast<const float4*>(lay + f.o_w1), L.NTH,
+                              lay + f.o_b1 + L.D8, [&](int nt, const float (&c)[4]) {
+                                  hidden_fwd<TP, false>(h1, nullptr, nt, g, t, c);
+                              });
+        }
+        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false);
         __syncthreads();
-        int KS = tile_gemm<T>(b.z1b, L.D1P / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w1),
-                              L.WP, b.red, L.red_floats);
-        tile_gemm_prefetch<T>(L.WP / 4 + 1, reinterpret_cast<const float4*>(lay + f.o_w2), L.WP,
-                              L.red_floats);
-        __syncthreads();
-        hidden_epilogue<T, true, false>(L, b.red, KS, L.WP, 0, b.h1, nullptr);
-        __syncthreads();
-        KS = mlp_tail<T, false>(L, b, lay, f, k, lay + f.o_mix_inv, L.DP / 4, L.DP);
-        for (int i = threadIdx.x; i < T * L.d2; i += FAB_NT) {
-            const int j = i / T, p = i - j * T;
-            const float shift = red_sum<T>(b.red, KS, L.P2, p, j);
-            const float scale = red_sum<T>(b.red, KS, L.P2, p, L.d2 + j);
-            const int e = kidx<T>(p, L.d1 + j);
-            b.zs[e] = b.zs[e] * expf(scale) + shift;
-            b.scl[p * L.d2 + j] = scale;
+        const int KSe = mlp_tail<TP, false>(L, lay, f, k, lay + f.o_mix_inv, L.D8 / 8, true);
+        {
+            const float* b3 = lay + f.o_b3;
+            float ssum = 0.f;
+            for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) {
+                const int j = e / TP, p = e - j * TP;
+                const float shift = red_sum<TP>(b.red, KSe, L.P8, p, j) + __ldg(b3 + j);
+                const float scale = red_sum<TP>(b.red, KSe, L.P8, p, L.d2 + j) + __ldg(b3 + L.d2 + j);
+                float* zp = z + (size_t)(L.d1 + j) * S + p;
+                *zp = *zp * expf(scale) + shift;
+                ssum += scale;
+            }
+            slot_partial<TP>(b, ssum);
         }
         __syncthreads();
         // log q -= sum(scale);  log q -= (-sum log_S)
-        logdet_accumulate<T>(L, b, b.logs[k]);
+        logdet_accumulate<TP>(b, b.logs[k]);
         // u' = [v1,y2] @ Wmix^-1
-        KS = tile_gemm<T>(b.zs, L.DP / 4, reinterpret_cast<const float4*>(lay + f.o_mix_inv), L.DP,
-                          b.red, L.red_floats);
+        const int KS2 = mma_gemm_ksplit<TP>(z, L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mix_inv),
+                                            L.D8 / 8, b.red);
         if (k + 1 < L.K)
-            tile_gemm_prefetch<T>(L.D1P / 4 + 1,
-                                  reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w1),
-                                  L.WP, L.red_floats);
+            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w1), L.NTH, false);
         __syncthreads();
-        for (int e = threadIdx.x; e < TP * L.d; e += FAB_NT) {
-            int p, n;
-            kdecode<T>(e, p, n);
-            if (p < T) b.zs[e] = red_sum<T>(b.red, KS, L.DP, p, n);
+        for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
+            const int j = e / TP, p = e - j * TP;
+            z[(size_t)j * S + p] = red_sum<TP>(b.red, KS2, L.D8, p, j);
         }
         __syncthreads();
     }
-    for (int p = threadIdx.x; p < T; p += FAB_NT) lq_out[p] = b.ld[p];
+    if (threadIdx.x < TP) lq_out[threadIdx.x] = b.ld[threadIdx.x];
     __syncthreads();
 }

@@ -75,9 +75,8 @@ __device__ __forceinline__ float gmm_row(const fab_target_desc& t, const float* 
 }
 
 // Evaluate the target for the T rows xs[T][ld]; lp_out[T] and gp[T][ld] (nullable) in shared.
-template <int T>
 __device__ __forceinline__ void target_tile(const fab_target_desc& t, const float* xs, int ld,
-                                            int d, float* lp_out, float* gp) {
+                                            int d, int T, float* lp_out, float* gp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int p = warp; p < T; p += FAB_NWARPS) {
         float lp;

@@ -25,95 +25,102 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, int d, const
 __device__ __forceinline__ void copy_tile(float* dst, const float* src, int n) {
     for (int i = threadIdx.x; i < n; i += FAB_NT) dst[i] = src[i];
 }
-// k4-major operand buffer (tile_gemm.cuh) <-> global rows / row-major shared tiles
-template <int T>
-__device__ __forceinline__ void load_rows_k4(float* dst, const float* __restrict__ src, int d, int DP,
-                                             long long row0, int np) {
-    for (int e = threadIdx.x; e < TileDims<T>::TP * DP; e += FAB_NT) {
-        int p, n;
-        kdecode<T>(e, p, n);
-        dst[e] = (p < np && n < d) ? __ldg(src + (row0 + p) * d + n) : 0.f;
+// operand buffer (mma_gemm.cuh: element (slot p, row j) at j*S + p) <-> global rows / row-major
+// shared tiles.  Slots >= np are fed zeros.
+template <int TP>
+__device__ __forceinline__ void load_rows_act(float* dst, const float* __restrict__ src, int d,
+                                              long long row0, int np) {
+    constexpr int S = ActL<TP>::S;
+    for (int e = threadIdx.x; e < d * TP; e += FAB_NT) {
+        const int j = e / TP, p = e - j * TP;
+        dst[(size_t)j * S + p] = p < np ? __ldg(src + (row0 + p) * d + j) : 0.f;
     }
 }
-template <int T>
-__device__ __forceinline__ void store_rows_k4(float* __restrict__ dst, int d, const float* src,
-                                              long long row0, int np) {
+template <int TP>
+__device__ __forceinline__ void store_rows_act(float* __restrict__ dst, int d, const float* src,
+                                               long long row0, int np) {
+    constexpr int S = ActL<TP>::S;
     for (int i = threadIdx.x; i < np * d; i += FAB_NT) {
         const int p = i / d, j = i - p * d;
-        dst[(row0 + p) * d + j] = src[kidx<T>(p, j)];
+        dst[(row0 + p) * d + j] = src[(size_t)j * S + p];
     }
 }
-template <int T>
-__device__ __forceinline__ void rows_to_k4(float* dst_k4, const float* src_rows, int DP) {
-    for (int e = threadIdx.x; e < TileDims<T>::TP * DP; e += FAB_NT) {
-        int p, n;
-        kdecode<T>(e, p, n);
-        dst_k4[e] = p < T ? src_rows[p * DP + n] : 0.f;
+template <int TP>
+__device__ __forceinline__ void rows_to_act(float* dst, const float* src_rows, int d, int DP, int T) {
+    constexpr int S = ActL<TP>::S;
+    for (int e = threadIdx.x; e < d * TP; e += FAB_NT) {
+        const int j = e / TP, p = e - j * TP;
+        dst[(size_t)j * S + p] = p < T ? src_rows[p * DP + j] : 0.f;
     }
 }
-template <int T>
-__device__ __forceinline__ void k4_to_rows(float* dst_rows, const float* src_k4, int DP) {
+template <int TP>
+__device__ __forceinline__ void act_to_rows(float* dst_rows, const float* src, int d, int DP, int T) {
+    constexpr int S = ActL<TP>::S;
     for (int i = threadIdx.x; i < T * DP; i += FAB_NT) {
-        const int p = i / DP, n = i - p * DP;
-        dst_rows[i] = src_k4[kidx<T>(p, n)];
+        const int p = i / DP, j = i - p * DP;
+        dst_rows[i] = j < d ? src[(size_t)j * S + p] : 0.f;
     }
 }
 
 // Evaluate log q (+grad), log p (+grad) at the rows x[T][DP] (shared, row-major, pads zero).
-// Outputs in shared: lq[T], lp[T], gq[T][DP], gp[T][DP] (the last two only when GRAD).
-template <int T, bool GRAD>
-__device__ void eval_point(const TileLayout& L, const TileBufs& b, const fab_flow_desc& f,
+// Outputs in shared: lq[TP], lp[T], gq[T][DP], gp[T][DP] (the last two only when GRAD).
+template <int TP, bool GRAD>
+__device__ void eval_point(const TileLayout& L, const fab_flow_desc& f,
                            const float* __restrict__ blob, const fab_target_desc& tgt,
                            const float* x, float* lq, float* lp, float* gq, float* gp) {
-    rows_to_k4<T>(b.zs, x, L.DP);
+    const TileBufs b = tile_bufs(L);
+    prof_mark(1);
+    rows_to_act<TP>(zsel(L, 0), x, L.d, L.DP, L.T);
     __syncthreads();
-    flow_inverse<T, GRAD>(L, b, f, blob, lq);
+    prof_mark(2);
+    flow_inverse<TP, GRAD>(L, f, blob, 0, lq);
     if (GRAD) {
-        flow_backward<T>(L, b, f, blob);
-        k4_to_rows<T>(gq, b.vs, L.DP);
+        flow_backward<TP>(L, f, blob);
+        act_to_rows<TP>(gq, b.gs, L.d, L.DP, L.T);
     }
-    target_tile<T>(tgt, x, L.DP, L.d, lp, GRAD ? gp : nullptr);
+    target_tile(tgt, x, L.DP, L.d, L.T, lp, GRAD ? gp : nullptr);
     __syncthreads();
+    prof_mark(17);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K1/K2  flow sample      K3/K4  flow log_prob (+ input gradient)
 // ---------------------------------------------------------------------------------------------
-template <int T>
+template <int TP>
 __global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_flow_sample(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
               const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ log_q,
               long long n) {
-    extern __shared__ __align__(16) float smem[];
-    const TileBufs b = tile_bufs(L, smem);
+    float* const smem = fab_smem;
+    const TileBufs b = tile_bufs(L);
     float* lq = smem + L.o_state;
-    const long long row0 = (long long)blockIdx.x * T;
-    const int np = (int)min((long long)T, n - row0);
-    tile_init<T>(L, b, f, blob);
-    load_rows_k4<T>(b.zs, eps, L.d, L.DP, row0, np);
+    const long long row0 = (long long)blockIdx.x * L.T;
+    const int np = (int)min((long long)L.T, n - row0);
+    tile_init(L, f, blob);
+    load_rows_act<TP>(zsel(L, 0), eps, L.d, row0, np);
     __syncthreads();
-    flow_sample<T>(L, b, f, blob, lq);
-    store_rows_k4<T>(x, L.d, b.zs, row0, np);
+    flow_sample<TP>(L, f, blob, 0, lq);
+    store_rows_act<TP>(x, L.d, zsel(L, 0), row0, np);
     for (int p = threadIdx.x; p < np; p += FAB_NT) log_q[row0 + p] = lq[p];
 }
 
-template <int T, bool GRAD>
+template <int TP, bool GRAD>
 __global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_flow_logprob(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
                const float* __restrict__ x, float* __restrict__ log_q, float* __restrict__ grad,
                long long n) {
-    extern __shared__ __align__(16) float smem[];
-    const TileBufs b = tile_bufs(L, smem);
+    float* const smem = fab_smem;
+    const TileBufs b = tile_bufs(L);
     float* lq = smem + L.o_state;
-    const long long row0 = (long long)blockIdx.x * T;
-    const int np = (int)min((long long)T, n - row0);
-    tile_init<T>(L, b, f, blob);
-    load_rows_k4<T>(b.zs, x, L.d, L.DP, row0, np);
+    const long long row0 = (long long)blockIdx.x * L.T;
+    const int np = (int)min((long long)L.T, n - row0);
+    tile_init(L, f, blob);
+    load_rows_act<TP>(zsel(L, 0), x, L.d, row0, np);
     __syncthreads();
-    flow_inverse<T, GRAD>(L, b, f, blob, lq);
+    flow_inverse<TP, GRAD>(L, f, blob, 0, lq);
     if (GRAD) {
-        flow_backward<T>(L, b, f, blob);
-        store_rows_k4<T>(grad, L.d, b.vs, row0, np);
+        flow_backward<TP>(L, f, blob);
+        store_rows_act<TP>(grad, L.d, b.gs, row0, np);
     }
     for (int p = threadIdx.x; p < np; p += FAB_NT) log_q[row0 + p] = lq[p];
 }
@@ -122,34 +129,36 @@ k_flow_logprob(TileLayout L, fab_flow_desc f, const float* __restrict__ blob,
 // chain initialisation (ais.py:56-65)
 // state area: x[T][DP], gq[T][DP], gp[T][DP], lq0[T], lq[T], lp[T]
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int init_state_floats(int T, int DP) { return 3 * T * DP + 3 * fab_round4(T); }
+__host__ __device__ inline int init_state_floats(int T, int DP) { return 3 * T * DP + 3 * 16; }
 
-template <int T, bool GRAD>
+template <int TP, bool GRAD>
 __global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_ais_init(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
            const float* __restrict__ eps, fab_gamma g1, fab_point out, float* __restrict__ log_w,
            float* __restrict__ log_q0, uint8_t* __restrict__ valid, long long n) {
-    extern __shared__ __align__(16) float smem[];
-    const TileBufs b = tile_bufs(L, smem);
+    float* const smem = fab_smem;
+    const TileBufs b = tile_bufs(L);
+    const int T = L.T;
     float* sx = smem + L.o_state;
     float* sgq = sx + T * L.DP;
     float* sgp = sgq + T * L.DP;
     float* slq0 = sgp + T * L.DP;
-    float* slq = slq0 + fab_round4(T);
-    float* slp = slq + fab_round4(T);
+    float* slq = slq0 + 16;
+    float* slp = slq + 16;
     const long long row0 = (long long)blockIdx.x * T;
     const int np = (int)min((long long)T, n - row0);
-    tile_init<T>(L, b, f, blob);
-    load_rows_k4<T>(b.zs, eps, L.d, L.DP, row0, np);
+    prof_mark(-1);
+    tile_init(L, f, blob);
+    load_rows_act<TP>(zsel(L, 0), eps, L.d, row0, np);
     __syncthreads();
-    flow_sample<T>(L, b, f, blob, slq0);
-    k4_to_rows<T>(sx, b.zs, L.DP);
+    flow_sample<TP>(L, f, blob, 0, slq0);
+    act_to_rows<TP>(sx, zsel(L, 0), L.d, L.DP, T);
     __syncthreads();
     if (GRAD) {
         // create_point(with_grad=True) re-evaluates log q by the inverse pass
-        eval_point<T, true>(L, b, f, blob, tgt, sx, slq, slp, sgq, sgp);
+        eval_point<TP, true>(L, f, blob, tgt, sx, slq, slp, sgq, sgp);
     } else {
-        target_tile<T>(tgt, sx, L.DP, L.d, slp, nullptr);
+        target_tile(tgt, sx, L.DP, L.d, T, slp, nullptr);
         for (int p = threadIdx.x; p < T; p += FAB_NT) slq[p] = slq0[p];
         __syncthreads();
     }
@@ -235,18 +244,19 @@ __global__ void k_hmc_finish(fab_hmc_state st, fab_hmc_args a, const float* __re
 // state area: cur{x,gq,gp}, prop{x,gq,gp}, mom : 7*[T][DP]; scalars cur_lq,cur_lp,prop_lq,prop_lp,
 // ke0, red2[4]
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int hmc_state_floats(int T, int DP) { return 7 * T * DP + 8 * fab_round4(T) + 8; }
+__host__ __device__ inline int hmc_state_floats(int T, int DP) { return 7 * T * DP + 8 * 16 + 8; }
 
-template <int T>
+template <int TP>
 __global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
            fab_hmc_state st, fab_hmc_args a, fab_point cur, fab_point prop_in, fab_point prop_out,
            float* __restrict__ log_w, const float* __restrict__ mom_noise,
            const float* __restrict__ exp_noise, const int* __restrict__ n_active,
            float* __restrict__ stats, float* ws, long long n) {
-    extern __shared__ __align__(16) float smem[];
-    const TileBufs b = tile_bufs(L, smem);
-    const int TD = T * L.DP, T4 = fab_round4(T);
+    float* const smem = fab_smem;
+    const TileBufs b = tile_bufs(L);
+    const int T = L.T;
+    const int TD = T * L.DP, T4 = 16;
     float* cx = smem + L.o_state;
     float* cgq = cx + TD;  float* cgp = cgq + TD;
     float* px = cgp + TD;  float* pgq = px + TD;  float* pgp = pgq + TD;
@@ -263,8 +273,9 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
     if (np < 0) np = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    prof_mark(-1);
     if (np > 0) {
-        tile_init<T>(L, b, f, blob);
+        tile_init(L, f, blob);
         load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
         load_rows(cgq, L.DP, cur.d_grad_log_q, L.d, row0, np, T);
         load_rows(cgp, L.DP, cur.d_grad_log_p, L.d, row0, np, T);
@@ -306,6 +317,7 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
             s = warp_sum(s);
             if (lane == 0) ke0[p] = 0.5f * s;
         }
+        prof_mark(0);
         // leapfrog (hmc.py:138-147)
         for (int l = 0; l < a.L; ++l) {
             for (int i = threadIdx.x; i < TD; i += FAB_NT) {
@@ -318,7 +330,7 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
                 }
             }
             __syncthreads();
-            eval_point<T, true>(L, b, f, blob, tgt, px, plq, plp, pgq, pgp);
+            eval_point<TP, true>(L, f, blob, tgt, px, plq, plp, pgq, pgp);
             for (int i = threadIdx.x; i < TD; i += FAB_NT) {
                 const int j = i % L.DP;
                 if (j < L.d) {
@@ -397,6 +409,7 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
         if (threadIdx.x < 2) blk[threadIdx.x] = 0.f;
     }
     __syncthreads();
+    prof_mark(18);
     if (grid_reduce_last<2>(blk, ws, blk + 4)) {
         if (threadIdx.x == 0) {
             stats[0] = blk[4]; stats[1] = (float)n_act; stats[2] = blk[5]; stats[3] = 0.f;
@@ -412,7 +425,7 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
 // ---------------------------------------------------------------------------------------------
 #define FAB_MAX_UPDATES 16
 __host__ __device__ inline int metro_state_floats(int T, int DP) {
-    return 2 * T * DP + 7 * fab_round4(T) + 4 * FAB_MAX_UPDATES;
+    return 2 * T * DP + 7 * 16 + 4 * FAB_MAX_UPDATES;
 }
 
 __device__ __forceinline__ void metropolis_finish(const fab_metropolis_args& a, float* scal,
@@ -430,15 +443,16 @@ __global__ void k_metropolis_finish(fab_metropolis_args a, float* scal,
         for (int u = 0; u < a.n_updates; ++u) metropolis_finish(a, scal, u, stats[2 * u], stats[2 * u + 1]);
 }
 
-template <int T>
+template <int TP>
 __global__ void __launch_bounds__(FAB_NT, FAB_MIN_CTAS)
 k_metropolis(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_target_desc tgt,
              fab_metropolis_args a, float* scal, fab_point cur, float* __restrict__ log_w,
              const float* __restrict__ prop_noise, const float* __restrict__ unif,
              const int* __restrict__ n_active, float* __restrict__ stats, float* ws, long long n) {
-    extern __shared__ __align__(16) float smem[];
-    const TileBufs b = tile_bufs(L, smem);
-    const int TD = T * L.DP, T4 = fab_round4(T);
+    float* const smem = fab_smem;
+    const TileBufs b = tile_bufs(L);
+    const int T = L.T;
+    const int TD = T * L.DP, T4 = 16;
     float* cx = smem + L.o_state;
     float* px = cx + TD;
     float* clq = px + TD;  float* clp = clq + T4;
@@ -452,7 +466,7 @@ k_metropolis(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_
     if (np < 0) np = 0;
     for (int u = threadIdx.x; u < 4 * FAB_MAX_UPDATES; u += FAB_NT) blk[u] = 0.f;
     if (np > 0) {
-        tile_init<T>(L, b, f, blob);
+        tile_init(L, f, blob);
         load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
         for (int p = threadIdx.x; p < T; p += FAB_NT) {
             const float lq = p < np ? cur.d_log_q[row0 + p] : 0.f;
@@ -471,7 +485,7 @@ k_metropolis(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_
                             : 0.f;
             }
             __syncthreads();
-            eval_point<T, false>(L, b, f, blob, tgt, px, plq, plp, nullptr, nullptr);
+            eval_point<TP, false>(L, f, blob, tgt, px, plq, plp, nullptr, nullptr);
             if (threadIdx.x < T) {
                 const int p = threadIdx.x;
                 float fl = 0.f, c_p = 0.f;

@@ -98,12 +98,34 @@ def _r4(v: int) -> int:
     return (v + 3) // 4 * 4
 
 
-def _pack_operand(M: torch.Tensor, Kpad: int, NP: int) -> torch.Tensor:
-    """M [Lyr, K, N] -> packed float4 operand [Lyr, Kpad/4 * NP * 4] (see include/fab_b200.h)."""
+def _r8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+def _r16(v: int) -> int:
+    return (v + 15) // 16 * 16
+
+
+def _round22(M: torch.Tensor) -> torch.Tensor:
+    """Round fp32 values to 22 significant bits = tf32 hi (top 11 bits, truncated) + tf32 lo (the
+    remainder rounded to nearest on the tf32 grid), so that the kernels' hi/lo operand split is
+    exact (mma_gemm.cuh: split_w).  Relative change <= 2^-23, unbiased."""
+    mask = -8192                                          # 0xffffe000 as int32
+    hi = (M.contiguous().view(torch.int32) & mask).view(torch.float32)
+    lo = M - hi
+    lo_r = ((lo.view(torch.int32) + 0x1000) & mask).view(torch.float32)
+    return hi + lo_r
+
+
+def _pack_frag(M: torch.Tensor, K16: int, N8: int) -> torch.Tensor:
+    """M [Lyr, K, N] -> MMA fragment order [Lyr, (K16/16)*(N8/8)*128] (see include/fab_b200.h):
+    Wf[kp][nt][lane = 4g+t] = (M[16kp+t][8nt+g], M[16kp+t+4][.], M[16kp+8+t][.], M[16kp+12+t][.])."""
     Lyr, K, N = M.shape
-    out = M.new_zeros(Lyr, Kpad, NP)
-    out[:, :K, :N] = M
-    return out.view(Lyr, Kpad // 4, 4, NP).permute(0, 1, 3, 2).reshape(Lyr, -1)
+    out = M.new_zeros(Lyr, K16, N8)
+    out[:, :K, :N] = _round22(M)
+    # k = 16*kp + 8*h + 4*half + t ; n = 8*nt + g  ->  [kp][nt][g][t][h][half]
+    v = out.view(Lyr, K16 // 16, 2, 2, 4, N8 // 8, 8)
+    return v.permute(0, 1, 5, 6, 4, 2, 3).reshape(Lyr, -1)
 
 
 def _pad_last(v: torch.Tensor, n: int) -> torch.Tensor:
@@ -177,12 +199,15 @@ class B200RealNVP(TrainableDistribution):
         dev = self._nf_model.q0.loc.device
         if self._nf_model.q0.loc.dtype != torch.float32:
             raise RuntimeError("B200RealNVP kernels are fp32; keep the flow in float32")
-        DP, D1P, P2, WP = _r4(d.dim), _r4(d.d1), _r4(2 * d.d2), d.width_pad
+        DP, D8, D16 = _r4(d.dim), _r8(d.dim), _r16(d.dim)
+        D1K, P8, P16 = _r16(d.d1), _r8(2 * d.d2), _r16(2 * d.d2)
+        W8, W16 = d.width_pad, d.width_kpad
         base = torch.cat([_pad_last(self._nf_model.q0.loc.reshape(-1), DP),
                           _pad_last(self._nf_model.q0.log_scale.reshape(-1), DP)])
         K = self.n_flow_layers
+        tail = base.new_zeros(512)
         if K == 0:
-            return base.contiguous()
+            return torch.cat([base, tail]).contiguous()
         blocks = [self._nf_model.flows[2 * k] for k in range(K)]
         W1 = torch.stack([b.linears[0].weight for b in blocks])     # [K, W, d1]
         b1 = torch.stack([b.linears[0].bias for b in blocks])
@@ -198,36 +223,31 @@ class B200RealNVP(TrainableDistribution):
         dd, d1, W = d.dim, d.d1, d.width
         z = lambda r, c: W1.new_zeros(K, r, c)
         # merged operands (products in float64, rounded once)
-        mw1 = z(DP + 4, DP + WP)                       # o_mw1: [z | 1] -> [v | h1pre]
-        mw1[:, :dd, :dd] = Wm
-        mw1[:, :dd, DP:DP + W] = (Wm[:, :, :d1].double() @ t(W1).double()).float()
-        mw1[:, DP, DP:DP + W] = b1
-        w2 = z(WP + 4, WP)                             # o_w2: [h1 | 1] -> h2pre
-        w2[:, :W, :W] = t(W2)
-        w2[:, WP, :W] = b2
-        w3 = z(WP + 4, P2)                             # o_w3: [h2 | 1] -> (shift | scale)
-        w3[:, :W, :2 * d.d2] = t(W3)
-        w3[:, WP, :2 * d.d2] = b3
-        w1mt = z(WP + DP, DP)                          # o_w1mt: [gh1 | gv] -> g_u
-        w1mt[:, :W, :dd] = (W1.double() @ t(Wm[:, :, :d1]).double()).float()
-        w1mt[:, WP:WP + dd, :dd] = t(Wm)
-        w1 = z(D1P + 4, WP)                            # o_w1 (sampling): [z1 | 1] -> h1pre
-        w1[:, :d1, :W] = t(W1)
-        w1[:, D1P, :W] = b1
+        mw1 = z(dd, D8 + W)                            # o_mw1: z -> [v | h1pre]
+        mw1[:, :, :dd] = Wm
+        mw1[:, :, D8:D8 + W] = (Wm[:, :, :d1].double() @ t(W1).double()).float()
+        w1mt = z(W16 + dd, dd)                         # o_w1mt: [gh1 | gv] -> g_u
+        w1mt[:, :W, :] = (W1.double() @ t(Wm[:, :, :d1]).double()).float()
+        w1mt[:, W16:W16 + dd, :] = t(Wm)
+        b1e = z(1, D8 + W8)[:, 0]                      # o_b1: [0 | b1]
+        b1e[:, D8:D8 + W] = b1
         parts = [
-            _pack_operand(mw1, DP + 4, DP + WP),
-            _pack_operand(w2, WP + 4, WP),
-            _pack_operand(w3, WP + 4, P2),
-            _pack_operand(W3, P2, WP),                 # o_w3t     M[k][n] = W3p[k][n]
-            _pack_operand(W2, WP, WP),                 # o_w2t     M[k][n] = W2[k][n]
-            _pack_operand(w1mt, WP + DP, DP),
-            _pack_operand(w1, D1P + 4, WP),
-            _pack_operand(Wm_inv, DP, DP),             # o_mix_inv
+            _pack_frag(mw1, D16, D8 + W8),
+            _pack_frag(t(W2), W16, W8),                # o_w2      M[k][n] = W2[n][k]
+            _pack_frag(t(W3), W16, P8),                # o_w3      M[k][n] = W3p[n][k]
+            _pack_frag(W3, P16, W8),                   # o_w3t     M[k][n] = W3p[k][n]
+            _pack_frag(W2, W16, W8),                   # o_w2t     M[k][n] = W2[k][n]
+            _pack_frag(w1mt, W16 + D16, D8),
+            _pack_frag(t(W1), D1K, W8),                # o_w1      M[k][n] = W1[n][k]
+            _pack_frag(Wm_inv, D16, D8),               # o_mix_inv
+            b1e,
+            _pad_last(b2, W8),
+            _pad_last(b3, P8),
             _pad_last(logs[:, None], 4),
         ]
         layers = torch.cat(parts, dim=1)
         assert layers.shape[1] == d.layer_stride, (layers.shape, d.layer_stride)
-        blob = torch.cat([base, layers.reshape(-1)]).contiguous()
+        blob = torch.cat([base, layers.reshape(-1), tail]).contiguous()
         assert blob.numel() == d.total_floats
         return blob
 

@@ -42,54 +42,60 @@ extern "C" {
  * :11-30,82-96 with act_norm=False:  DiagGaussian base, then n_layers x { AffineCouplingBlock(
  * MLP[d1 -> W -> W -> 2*d2], exp scale map), InvertibleAffine(d) }.
  *
- * Every dense matrix is stored as a "packed operand" for out[p][n] = sum_k act[p][k] * M[k][n]:
- *      float4 Wp[K4][NP];   Wp[k4][n].{x,y,z,w} = M[4*k4 + {0,1,2,3}][n]    (0 beyond K or N)
- *      K4 = ceil(K/4), NP = round_up(N, 4)
- * so that consecutive threads (consecutive n) read consecutive 16-byte words.
- * The hidden width is padded to WP = round_up(W, 4) with zero weights/biases.
+ * Every dense matrix M of out[p][n] = sum_k act[p][k] * M[k][n] is stored in MMA FRAGMENT ORDER
+ * for the warp-level tensor instruction mma.sync.m16n8k8 (TF32):
+ *      float4 Wf[KT2][NT][32];     KT2 = K16/16 k-tile pairs, NT = N8/8 n-tiles, 32 lanes
+ *      Wf[kp][nt][lane] = { M[16kp+t][8nt+g], M[16kp+t+4][8nt+g],
+ *                           M[16kp+8+t][8nt+g], M[16kp+12+t][8nt+g] }   g = lane>>2, t = lane&3
+ * (0 beyond K or N), i.e. the B fragments of two consecutive k-tiles: a warp reads one coalesced
+ * 512-byte line per (k-tile pair, n-tile).  K is padded to K16 = round_up(K,16), N to
+ * N8 = round_up(N,8).  Values are plain fp32; the kernels split them into tf32 hi/lo parts on
+ * the fly (3xTF32, fp32-grade accuracy).
  *
- * Biases are folded into the GEMMs: an operand whose input is an activation buffer carries one
- * extra k4 block whose first row is the bias (other three rows 0); the kernels keep a constant
- * (1,0,0,0) block at the end of the corresponding activation buffer.  The d x d mixing matrix of
+ * Biases are separate vectors (they initialise the accumulators).  The d x d mixing matrix of
  * each InvertibleAffine is merged into the neighbouring MLP GEMM (one GEMM + one barrier pair less
  * per layer pass in both directions); the merged products are formed in float64 on the host.
  *
- * Blob layout (float offsets):  [base block][layer 0 block][layer 1 block]...
+ * Blob layout (float offsets):  [base block][layer 0 block][layer 1 block]...[512 floats pad]
  *   base block : loc[DP], log_scale[DP]                         DP = round_up(d,4)
  *   layer block (all offsets relative to the layer block start; layer k of the reference's
  *   flow list, k = 0 is applied first when sampling).  W1 [W,d1], W2 [W,W], W3 [2*d2,W] are the
  *   nn.Linear weights ([out,in]); W3p/b3p = W3/b3 with rows de-interleaved (first the d2 shift
- *   rows 0,2,4.., then the d2 scale rows 1,3,5..); P2 = round_up(2*d2,4), D1P = round_up(d1,4).
+ *   rows 0,2,4.., then the d2 scale rows 1,3,5..).  D8/D16 = round_up(d,8/16), W8/W16 likewise
+ *   for W, P8/P16 for 2*d2, D1K = round_up(d1,16).
  *   inverse direction (log_prob):
- *     o_mw1   K=DP+4  N=DP+WP  in = [z | 1]            out = [v = z@Wmix | h1pre]
- *                              M[k<d][n<d] = Wmix[k][n];  M[k<d][DP+j] = (Wmix[:, :d1] @ W1^T)[k][j];
- *                              M[DP][DP+j] = b1[j]
- *     o_w2    K=WP+4  N=WP     in = [h1 | 1]           M[k][n] = W2[n][k];   M[WP][n] = b2[n]
- *     o_w3    K=WP+4  N=P2     in = [h2 | 1]           M[k][n] = W3p[n][k];  M[WP][n] = b3p[n]
+ *     o_mw1   K16=D16     N8=D8+W8  in = z       out = [v = z@Wmix | h1pre]
+ *                              M[k<d][n<d] = Wmix[k][n];  M[k<d][D8+j] = (Wmix[:, :d1] @ W1^T)[k][j]
+ *     o_w2    K16=W16     N8=W8     in = h1      M[k][n] = W2[n][k]
+ *     o_w3    K16=W16     N8=P8     in = h2      M[k][n] = W3p[n][k]
  *   input-gradient sweep:
- *     o_w3t   K=P2    N=WP     in = gparam             M[k][n] = W3p[k][n]
- *     o_w2t   K=WP    N=WP     in = gh2                M[k][n] = W2[k][n]
- *     o_w1mt  K=WP+DP N=DP     in = [gh1 | gv]         M[k<W][n] = (W1 @ Wmix[:, :d1]^T)[k][n];
- *                                                      M[WP+i][n] = Wmix[n][i]      (g @ Wmix^T)
+ *     o_w3t   K16=P16     N8=W8     in = gparam  M[k][n] = W3p[k][n]
+ *     o_w2t   K16=W16     N8=W8     in = gh2     M[k][n] = W2[k][n]
+ *     o_w1mt  K16=W16+D16 N8=D8     in = [gh1 | gv]   M[k<W][n] = (W1 @ Wmix[:, :d1]^T)[k][n];
+ *                                                     M[W16+i][n] = Wmix[n][i]      (g @ Wmix^T)
  *   sampling direction:
- *     o_w1    K=D1P+4 N=WP     in = [z1 | 1]           M[k][n] = W1[n][k];   M[D1P][n] = b1[n]
- *     o_mix_inv K=DP  N=DP     in = [v1,y2]            M[k][n] = Wmix^-1[k][n]
+ *     o_w1    K16=D1K     N8=W8     in = z1      M[k][n] = W1[n][k]
+ *     o_mix_inv K16=D16   N8=D8     in = [v1,y2] M[k][n] = Wmix^-1[k][n]
  *     (o_w2, o_w3 are shared with the inverse direction)
- *     o_logs[4] : [0] = sum(log_S) of this layer's InvertibleAffine
+ *   vectors:
+ *     o_b1[D8+W8] = [0 (D8) | b1 (W8)]   (o_b1 + D8 is the plain b1 of the sampling direction)
+ *     o_b2[W8] = b2;   o_b3[P8] = b3p;   o_logs[4] : [0] = sum(log_S) of this layer's InvertibleAffine
  * ------------------------------------------------------------------------------------- */
 typedef struct fab_flow_desc {
     int32_t dim;          /* d                                   */
     int32_t d1;           /* int(d/2 + 0.5): conditioner input   */
     int32_t d2;           /* d - d1: transformed half            */
     int32_t width;        /* W  (as given by the caller)         */
-    int32_t width_pad;    /* WP = round_up(W,4)                  */
+    int32_t width_pad;    /* W8  = round_up(W,8)  (n-tiles)      */
+    int32_t width_kpad;   /* W16 = round_up(W,16) (k-tile pairs) */
     int32_t n_layers;     /* coupling blocks; 0 = plain diagonal Gaussian */
     int64_t total_floats; /* blob size                           */
     int64_t off_base_loc, off_base_log_scale;
     int64_t off_layers, layer_stride;
     int64_t o_mw1, o_w2, o_w3;
     int64_t o_w3t, o_w2t, o_w1mt;
-    int64_t o_w1, o_mix_inv, o_logs;
+    int64_t o_w1, o_mix_inv;
+    int64_t o_b1, o_b2, o_b3, o_logs;
 } fab_flow_desc;
 
 /* Fills every field of *desc from (dim, width, n_layers); returns total_floats or <0. */

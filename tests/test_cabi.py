@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound(L):
 
 def test_struct_sizes_match_header(L):
     # natural C alignment of the header structs
-    assert C.sizeof(_lib.FlowDesc) == 6 * 4 + 14 * 8
+    assert C.sizeof(_lib.FlowDesc) == 8 * 4 + 17 * 8      # 7 int32 + pad, 17 int64
     assert C.sizeof(_lib.Gamma) == 16
     assert C.sizeof(_lib.PointPtrs) == 40
     assert C.sizeof(_lib.TargetDesc) == 8 * 4 + 3 * 8
@@ -47,13 +47,16 @@ def test_flow_desc_init(L):
     d = _lib.FlowDesc()
     n = L.fab_flow_desc_init(d, 32, 320, 10)
     assert n == d.total_floats > 0
-    assert (d.dim, d.d1, d.d2, d.width_pad, d.n_layers) == (32, 16, 16, 320, 10)
-    # o_mw1 (36x352) o_w2 (324x320) o_w3 (324x32) o_w3t (32x320) o_w2t (320x320) o_w1mt (352x32)
-    # o_w1 (20x320) o_mix_inv (32x32) o_logs (4)
-    per_layer = 36 * 352 + 324 * 320 + 324 * 32 + 32 * 320 + 320 * 320 + 352 * 32 + 20 * 320 + 32 * 32 + 4
+    assert (d.dim, d.d1, d.d2, d.width_pad, d.width_kpad, d.n_layers) == (32, 16, 16, 320, 320, 10)
+    # fragment-ordered operands (K16 x N8): o_mw1 (32x352) o_w2 (320x320) o_w3 (320x32)
+    # o_w3t (32x320) o_w2t (320x320) o_w1mt (352x32) o_w1 (16x320) o_mix_inv (32x32);
+    # vectors o_b1 (352) o_b2 (320) o_b3 (32) o_logs (4)
+    per_layer = (32 * 352 + 320 * 320 + 320 * 32 + 32 * 320 + 320 * 320 + 352 * 32 + 16 * 320 + 32 * 32
+                 + 352 + 320 + 32 + 4)
     assert d.layer_stride == per_layer
-    assert d.total_floats == 64 + 10 * per_layer
-    assert L.fab_flow_desc_init(d, 5, 15, 2) > 0 and (d.d1, d.d2, d.width_pad) == (3, 2, 16)
+    assert d.total_floats == 64 + 10 * per_layer + 512
+    assert L.fab_flow_desc_init(d, 5, 15, 2) > 0
+    assert (d.d1, d.d2, d.width_pad, d.width_kpad) == (3, 2, 16, 16)
     assert L.fab_flow_desc_init(d, 1, 10, 1) < 0
     assert b"dim>=2" in L.fab_last_error()
 

@@ -27,7 +27,7 @@ def test_log_prob_and_grad(dim, K, npd, n):
     assert none is None
     assert_parity(lq, lq_ref, lq_32, "log_q")
     assert_parity(lq_only, lq_ref, lq_32, "log_q (value only)")
-    assert_parity(grad, g_ref, g_32, "grad_log_q", floor=5e-5)
+    assert_parity(grad, g_ref, g_32, "grad_log_q", floor=5e-5, outlier_frac=0.005)   # ReLU kinks
 
 
 @pytest.mark.parametrize("dim,K,npd", CASES)

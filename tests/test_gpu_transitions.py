@@ -4,7 +4,10 @@ same fp32 Point and consume the same noise, so differences are rounding only (SU
 bar (1e-5 relative, or no worse than 4x the reference's own fp32 CPU run); Metropolis is compared
 with the fp32 oracle because its `exp(gamma' - gamma)` overflow -> reject rule (metropolis.py:63-64)
 triggers at 88.7 in fp32 but not in fp64.  A particle whose accept test lands within rounding of
-the threshold may flip; at most 1 % such flips are tolerated and excluded from value comparison."""
+the threshold may flip; at most 1 % such flips are tolerated and excluded from value comparison.
+Likewise at most 1 % of the particles may sit on a ReLU kink of the flow during the leapfrog (the
+gradient is discontinuous there; helpers.assert_parity `outlier_frac`) and must stay within 100x
+the bar."""
 import copy
 
 import pytest
@@ -83,7 +86,8 @@ def test_hmc_transition(dim, K, npd, tk, M, i, L, n_outer, eps, p_target, alpha,
     for name, floor in (("x", 1e-5), ("log_q", 1e-5), ("log_p", 1e-5), ("grad_log_q", 1e-4),
                         ("grad_log_p", 1e-4)):
         report[name] = assert_parity(getattr(out_p, name), getattr(out_o, name),
-                                     getattr(out_32, name), name, floor=floor, mask=ok)
+                                     getattr(out_32, name), name, floor=floor, mask=ok,
+                                     outlier_frac=0.01)
     print(f"\nHMC d={dim} i={i}: (cuda err, cpu-fp32 err) {report}; flips {int(fl.sum())}")
     # tuner state and logging scalars
     assert rel_err(op_p.epsilons, op_o.epsilons) < 1e-6
