@@ -10,7 +10,10 @@
 #include <stdint.h>
 #include "fab_b200.h"
 
-#define FAB_NT 256              // threads per tile CTA: 8 warps, fixed by the warp->tile maps of mma_gemm.cuh
+#ifndef FAB_NT
+#define FAB_NT 256              // threads per tile CTA (256 or 512).  8 warps measured faster than 16:
+                                // the operand splits of the shared A fragments are repeated per warp
+#endif
 #ifndef FAB_MIN_CTAS
 #define FAB_MIN_CTAS 1          // co-resident tile CTAs per SM the kernels are compiled for
 #endif
@@ -69,12 +72,12 @@ __host__ __device__ __forceinline__ int fab_round8(int v) { return (v + 7) & ~7;
 __host__ __device__ __forceinline__ int fab_round16(int v) { return (v + 15) & ~15; }
 
 // k-split plan of the narrow GEMMs (mma_gemm.cuh: mma_gemm_ksplit): NT n-tiles are spread over
-// NGR warp groups (<= 4 tiles per warp and pass), the remaining factor of the 8 warps splits K.
+// NGR warp groups (<= 4 tiles per warp and pass), the remaining factor of the warps splits K.
 __host__ __device__ inline void fab_ksplit_plan(int NT, int& NGR, int& KS) {
     const int need = (NT + 3) / 4;
     NGR = 1;
-    while (NGR < need && NGR < 8) NGR <<= 1;
-    KS = 8 / NGR;
+    while (NGR < need && NGR < FAB_NWARPS) NGR <<= 1;
+    KS = FAB_NWARPS / NGR;
 }
 
 // state_floats: extra per-CTA floats the calling kernel wants after the evaluation buffers.

@@ -168,7 +168,10 @@ __device__ __forceinline__ void mma_gemm_wide(const float* act, int KT2, const f
         }
     };
     // three-deep register ring: the main loop is unrolled by three so that no register moves are
-    // needed; each buffer is refilled (for the pair three steps ahead) right after its use
+    // needed; each buffer is refilled (for the pair three steps ahead) right after its use.
+    // (profiles/microbench_mma_variants.cu times the alternatives in isolation -- two-deep ring,
+    // packed f32x2 adds/splits, k-tile software pipelining, 16 warps: none beats this form in
+    // the full kernel, where the deeper prefetch also covers the short GEMMs' L2 latency.)
     float4 w0[FAB_NTW] = {}, w1[FAB_NTW] = {}, w2[FAB_NTW] = {};
     fetch(w0);
     fetch(w1);
