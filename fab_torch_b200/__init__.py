@@ -9,6 +9,7 @@ from fab_torch_b200.transition_operators import (TransitionOperator, Hamiltonian
                                                   make_gamma)
 from fab_torch_b200.ais import AnnealedImportanceSampler, LoggingInfo, setup_distribution_spacing
 from fab_torch_b200.numerical import effective_sample_size
-from fab_torch_b200.resample import systematic_resample, systematic_ancestors
+from fab_torch_b200.resample import (systematic_resample, systematic_ancestors,
+                                      global_systematic_resample, resample_if_ess_below)
 
 __version__ = "0.1"

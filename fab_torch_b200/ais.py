@@ -213,6 +213,16 @@ class AnnealedImportanceSampler:
             log_w = log_w[:n_end]
         return pt, log_w.detach()
 
+    def resample_if_ess_below(self, point: Point, log_w: torch.Tensor, threshold: float,
+                              u0: Optional[int] = None):
+        """Global ESS / resample trigger (build-side extension): uses the
+        all-reduced `ess_ais` of the last `sample_and_log_weights` call; below `threshold` the
+        (rank-sharded) particle set is resampled systematically with the bit-exact integer kernel
+        and the weights are reset to the mean weight.  Returns (point, log_w, resampled?)."""
+        from fab_torch_b200.resample import resample_if_ess_below
+        return resample_if_ess_below(point, log_w, self._logging_info.ess_ais, threshold, u0,
+                                     self.process_group)
+
     # kept for API parity with the reference sampler (ais.py:90-105); runs one fused transition
     def perform_transition(self, x_new: Point, log_w: torch.Tensor, j: int):
         x_new = self.transition_operator.run(x_new, j, self.B_space[j], log_w, self._w_update(j))

@@ -26,6 +26,8 @@ __host__ __device__ __forceinline__ int fab_round4(int v) { return (v + 3) & ~3;
 // profiles/phase_profile.py).  prof_mark(id) charges the cycles since the previous mark to `id`.
 #ifdef FAB_PROF
 __device__ unsigned long long g_fab_prof[32];
+__device__ unsigned long long g_fab_cta_cycles[1024];      // per-CTA cycles of the last k_hmc_step
+__device__ unsigned int g_fab_cta_smid[1024];
 __device__ __forceinline__ void prof_mark(int id) {
     __shared__ long long s_prof_last;
     if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -412,6 +412,12 @@ int fab_debug_prof(unsigned long long* out32, int reset) {
     }
     return FAB_OK;
 }
+int fab_debug_cta_cycles(unsigned long long* out1024, unsigned int* smid1024) {
+    if (cudaMemcpyFromSymbol(out1024, g_fab_cta_cycles, sizeof(unsigned long long) * 1024) != cudaSuccess ||
+        cudaMemcpyFromSymbol(smid1024, g_fab_cta_smid, sizeof(unsigned int) * 1024) != cudaSuccess)
+        return FAB_E_CUDA;
+    return FAB_OK;
+}
 #endif
 
 }  // extern "C"

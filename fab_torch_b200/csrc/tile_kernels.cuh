@@ -274,6 +274,9 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     prof_mark(-1);
+#ifdef FAB_PROF
+    const long long cta_t0 = clock64();
+#endif
     if (np > 0) {
         tile_init(L, f, blob);
         load_rows(cx, L.DP, cur.d_x, L.d, row0, np, T);
@@ -410,6 +413,13 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
     }
     __syncthreads();
     prof_mark(18);
+#ifdef FAB_PROF
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        g_fab_cta_cycles[blockIdx.x] = (unsigned long long)(clock64() - cta_t0);
+        unsigned int smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_fab_cta_smid[blockIdx.x] = smid;
+    }
+#endif
     if (grid_reduce_last<2>(blk, ws, blk + 4)) {
         if (threadIdx.x == 0) {
             stats[0] = blk[4]; stats[1] = (float)n_act; stats[2] = blk[5]; stats[3] = 0.f;

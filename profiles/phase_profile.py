@@ -43,3 +43,16 @@ print(f"CTA 0, {launches} k_hmc_step launches (+ k_ais_init's eval): {tot} cycle
       f"= {tot / 1.965e6:.2f} ms at 1965 MHz")
 for i in sorted(NAMES):
     print(f"{i:2d} {NAMES[i]:34s} {buf[i]:12d} cyc  {100.0 * buf[i] / tot:5.1f} %")
+
+# per-CTA duration of the last k_hmc_step launch (SM-to-SM spread)
+cyc = (ctypes.c_ulonglong * 1024)()
+smid = (ctypes.c_uint * 1024)()
+lib.fab_debug_cta_cycles.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_uint)]
+assert lib.fab_debug_cta_cycles(cyc, smid) == 0
+n_cta = (B + fb._lib.lib().fab_tile_particles(flow.desc(), B) - 1) // fb._lib.lib().fab_tile_particles(flow.desc(), B)
+v = sorted((cyc[i], smid[i], i) for i in range(n_cta))
+med = v[len(v) // 2][0]
+print(f"per-CTA cycles of the last launch ({n_cta} CTAs): min {v[0][0]}  median {med}  max {v[-1][0]} "
+      f"(max/median {v[-1][0] / med:.3f})")
+print("slowest (cycles, smid, cta):", v[-6:])
+print("fastest (cycles, smid, cta):", v[:4])

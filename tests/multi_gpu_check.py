@@ -73,6 +73,14 @@ def main():
               "average_distance_dist0"):
         ok &= abs(info_s[k] - info_1[k]) <= 1e-5 * max(1.0, abs(info_1[k]))
     ok &= torch.allclose(eps_s[0], op1.epsilons) and torch.allclose(eps_s[1], op1.common_epsilon)
+    # global ESS trigger + systematic resample over the ranks (BASELINE config 3): every rank must
+    # receive its slice of the single-device resample of the whole batch, bit for bit
+    u0 = 987654321
+    pt_r, lw_r, did = ais.resample_if_ess_below(pt_s, lw_s, threshold=1.1, u0=u0)      # always fires
+    pt_w, lw_w, did1 = ais1.resample_if_ess_below(pt_1, lw_1, threshold=1.1, u0=u0)
+    ok &= bool(did) and bool(did1)
+    ok &= torch.equal(pt_r.x, pt_w.x[sl]) and torch.equal(pt_r.grad_log_q, pt_w.grad_log_q[sl])
+    ok &= torch.allclose(lw_r, lw_w[sl])
     flag = torch.tensor([1.0 if ok else 0.0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

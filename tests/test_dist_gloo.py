@@ -57,6 +57,39 @@ def _worker(rank, world_size, port, out):
         assert float(stats[1]) == B
         assert abs(float(stats[0]) - (0.3 * B + sum(range(world_size)))) < 1e-4
         out[rank] = (float(ess), float(lse), float(stats[0]))
+        # global systematic resample over ragged shards (rank 0 lost 3 particles to the NaN
+        # filter): every rank must receive exactly its slice of the single-device answer.  The
+        # ancestor routine is injected: on a GPU it is the integer kernel, here the oracle.
+        import numpy as np
+        from oracle.resample import systematic_ancestors as oracle_anc
+        from fab_torch_b200.point import Point
+        from fab_torch_b200.resample import global_systematic_resample, resample_if_ess_below
+        counts = [n_local - 3, n_local] if world_size == 2 else [n_local] * world_size
+        offs = [sum(counts[:r]) for r in range(world_size + 1)]
+        N = offs[-1]
+        gg = torch.Generator().manual_seed(11)
+        X = torch.randn(N, 5, generator=gg)
+        LW = torch.randn(N, generator=gg) * 3
+        LW[7] = float("-inf")                                    # zero-weight particle
+        mine = slice(offs[rank], offs[rank + 1])
+        pt = Point(X[mine].clone(), LW[mine].clone() * 2, LW[mine].clone() * 3, X[mine].clone() + 1, None)
+        anc_fn = lambda lw, u0: torch.from_numpy(oracle_anc(lw.numpy(), u0))
+        u0 = 123456789
+        new_pt, anc, lw_new = global_systematic_resample(pt, LW[mine].clone(), u0, group, anc_fn)
+        want = torch.from_numpy(oracle_anc(LW.numpy(), u0))[mine]
+        assert torch.equal(anc, want)
+        assert torch.equal(new_pt.x, X[want]) and torch.equal(new_pt.log_q, (LW * 2)[want])
+        assert torch.equal(new_pt.grad_log_q, (X + 1)[want]) and new_pt.grad_log_p is None
+        assert 7 not in set(want.tolist())
+        mean_w = torch.logsumexp(LW.double(), 0) - np.log(N)
+        assert lw_new.shape == (counts[rank],) and abs(float(lw_new[0]) - float(mean_w)) < 1e-5
+        # trigger: above the threshold nothing happens, below every rank resamples
+        same = resample_if_ess_below(pt, LW[mine], ess=0.9, threshold=0.5, u0=u0, group=group,
+                                     ancestors_fn=anc_fn)
+        assert same[2] is False and same[0] is pt
+        trig = resample_if_ess_below(pt, LW[mine], ess=0.1, threshold=0.5, u0=u0, group=group,
+                                     ancestors_fn=anc_fn)
+        assert trig[2] is True and torch.equal(trig[0].x, X[want])
     finally:
         dist.destroy_process_group()
 

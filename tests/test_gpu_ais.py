@@ -14,8 +14,9 @@ from oracle.sampler import OracleAIS, OracleHMC, OracleMetropolis
 pytestmark = pytest.mark.gpu
 
 
-def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, alpha=2.0, **opkw):
-    fo64, fo, fp = make_flows(dim, K, npd, last_std=0.05)
+def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, alpha=2.0,
+              last_std=0.05, **opkw):
+    fo64, fo, fp = make_flows(dim, K, npd, last_std=last_std)
     if tk == "mw":
         to, tp = make_manywell(dim)
         to32 = to
@@ -60,6 +61,11 @@ AIS_CASES = [
          max_step_size=5.0, min_step_size=5.0, adjust_step_size=False),                     # config 1
     dict(dim=2, K=0, npd=1, tk="gmm", M=12, B=300, op_kind="hmc", spacing="geometric",
          p_target=True, alpha=None, epsilon=0.5, L=4, n_outer=2),
+    # BASELINE config 4 architecture (Many-Well-128, 10 layers x width 1280: the 8-slot tile
+    # layout, 160 MB of weights streamed from HBM/L2), shortened chain
+    dict(dim=128, K=10, npd=10, tk="mw", M=2, B=24, op_kind="hmc", epsilon=0.02, L=2, last_std=0.003),
+    # BASELINE config 5 shape (60-dof target, 20 distributions) on the many-well energy
+    dict(dim=60, K=4, npd=5, tk="mw", M=20, B=64, op_kind="hmc", epsilon=0.05, L=4),
 ]
 
 

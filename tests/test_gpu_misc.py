@@ -125,3 +125,27 @@ def test_systematic_resample_point_and_properties():
     # uniform weights with any offset -> identity permutation (idempotence)
     anc_u = fb.systematic_ancestors(torch.zeros(n).cuda(), 12345)
     assert torch.equal(anc_u.cpu(), torch.arange(n))
+
+
+def test_global_resample_and_ess_trigger_single_process():
+    """resample.global_systematic_resample / resample_if_ess_below without a process group reduce
+    to the single-device kernel (the multi-rank wiring is covered by tests/test_dist_gloo.py and
+    tests/multi_gpu_check.py); weights are reset to the mean weight."""
+    n, d = 2048, 32
+    g = torch.Generator().manual_seed(5)
+    lw = (torch.randn(n, generator=g) * 6 + 50).cuda()
+    pt = fb.Point(torch.randn(n, d, generator=g).cuda(), torch.randn(n, generator=g).cuda(),
+                  torch.randn(n, generator=g).cuda(), None, None)
+    u0 = 2 ** 31 + 7
+    want = oracle_ancestors(lw.cpu().numpy(), u0)
+    new, anc, lw_new = fb.global_systematic_resample(pt, lw, u0)
+    assert np.array_equal(anc.cpu().numpy(), want)
+    assert torch.equal(new.x, pt.x[anc]) and new.grad_log_q is None
+    mean_w = torch.logsumexp(lw.double(), 0).item() - np.log(n)
+    assert torch.allclose(lw_new, torch.full_like(lw_new, mean_w), atol=1e-4)
+    ess = float(fb.effective_sample_size(lw))
+    keep = fb.resample_if_ess_below(pt, lw, ess, threshold=ess * 0.5, u0=u0)
+    assert keep[2] is False and keep[0] is pt
+    res = fb.resample_if_ess_below(pt, lw, ess, threshold=min(1.0, ess * 2), u0=u0)
+    assert res[2] is True and torch.equal(res[0].x, new.x)
+    assert float(fb.effective_sample_size(res[1])) > 0.999         # uniform weights afterwards
