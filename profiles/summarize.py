@@ -90,11 +90,13 @@ def main():
     lines += [f"* duration {g('gpu__time_duration.sum')} {units.get('gpu__time_duration.sum')}, grid {g('launch__grid_size')}, "
               f"{g('launch__registers_per_thread')} regs/thread, dynamic smem {g('launch__shared_mem_per_block_dynamic')} KB",
               f"* DRAM traffic per launch: read {dr / 1e6:.2f} MB + write {dw / 1e6:.2f} MB = **{(dr + dw) / 1e6:.2f} MB** "
-              f"(algorithmic Point+noise bytes: 2048 x 924 B = 1.89 MB; the 10.3 MB weight blob is read once then L2-resident)",
+              f"(algorithmic Point+noise bytes: 2048 x 924 B = 1.89 MB; the 10.2 MB weight blob is read once then L2-resident)",
               f"* L2: tex read sectors {g('lts__t_sectors_srcunit_tex_op_read.sum')} (x32 B), hit rate {g('lts__t_sector_hit_rate.pct')} %",
               f"* FMA pipe active {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')} %, issue slots busy "
               f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} %, warps active {g('sm__warps_active.avg.pct_of_peak_sustained_active')} % of max",
-              f"* tensor pipe: {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} % (not used: fp32 parity bar, see DESIGN.md §4)",
+              f"* tensor pipe (warp-level HMMA.1688.F32.TF32, 3xTF32): active {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} % of cycles; "
+              f"ALU pipe {g('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active')} %; SM clock during the capture "
+              f"{g('sm__cycles_elapsed.avg.per_second')} {units.get('sm__cycles_elapsed.avg.per_second')}",
               f"* instructions {g('smsp__inst_executed.sum')}; mix: " + ", ".join(f"{k} {100 * v:.1f} %" for k, v in ops.items()),
               "* warp-stall samples: " + ", ".join(f"{k} {100 * v:.1f} %" for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:9]), ""]
     if bench:
@@ -102,15 +104,19 @@ def main():
         lines += ["## bench.py line of the same build", "",
                   f"* value {bench['value']:.0f} particles/s ({bench['ms_per_step']:.2f} ms/step), e2e {bench['e2e']['value']:.0f} particles/s",
                   f"* `k_hmc_step` {r['kernel_ms']:.3f} ms/launch (CUDA events) -> {r['achieved']:.2f} TFLOP/s algorithmic = "
-                  f"{100 * r['pipe_frac']:.1f} % of the FP32 FMA ceiling ({r['pipe_peak']:.1f} TF), {100 * r['frac']:.2f} % of measured bf16 tensor peak",
+                  f"{100 * r['pipe_frac']:.1f} % of the 3xTF32 mma.sync ceiling ({r['pipe_peak']:.1f} TF = measured HMMA issue rate / 3), "
+                  f"{100 * r['frac']:.2f} % of the measured bf16 cuBLAS peak",
                   f"* kernel share of the step: {100 * bench['config']['M'] * r['kernel_ms'] / bench['ms_per_step']:.1f} % (events) vs "
-                  f"{100 * by.get('k_hmc_step<14>', by.get('k_hmc_step', [0, 0]))[1] / tot if tot else 0:.1f} % (ncu launch list)",
+                  f"{100 * sum(v[1] for k, v in by.items() if k.startswith('k_hmc_step')) / tot if tot else 0:.1f} % (ncu launch list)",
                   f"* clocks: {bench.get('clocks')}", ""]
         if "cpu_baseline" in bench:
             lines += [f"* cpu_baseline: {bench['cpu_baseline']}", ""]
+        if "parity" in bench:
+            lines += [f"* parity (CUDA vs CPU port, identical injected noise): {bench['parity']}", ""]
     json.dump({"round": rnd, "kernel": "k_hmc_step", "dram_bytes_per_launch": dr + dw,
                "duration_ms_under_ncu": float(g("gpu__time_duration.sum")),
                "fma_pipe_active_pct": float(g("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")),
+               "tensor_pipe_active_pct": float(g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")),
                "issue_active_pct": float(g("smsp__issue_active.avg.pct_of_peak_sustained_active"))},
               open(os.path.join(HERE, f"{rnd}_metrics.json"), "w"), indent=1)
     open(os.path.join(HERE, f"{rnd}_summary.md"), "w").write("\n".join(lines))
