@@ -4,7 +4,7 @@
 //  (1) raw issue rate of mma.sync.m16n8k8.tf32 per SM sub-partition (independent accumulators)
 //  (2) a 3xTF32 (error-compensated, ~fp32 accurate) [16 x 320] x [320 x 320] tile GEMM: weights
 //      stream from L2 in fragment order, activations come from shared memory, hi/lo split on the
-//      fly -- the same job tile_gemm<14> does with FFMA2 in ~21.6k cycles.
+//      fly -- the job the first (FP32 FFMA2) version of the tile GEMM did in ~21.6k cycles.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/mb_hmma profiles/microbench_hmma.cu
 #include <cstdio>
 #include <cstdint>
@@ -166,7 +166,7 @@ int main() {
             }
             CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
             printf("3xTF32 tile GEMM [16x320]x[320x320], presplit_A=%d grid=%3d: %.0f cycles per GEMM "
-                   "(FFMA2 tile_gemm<14>: ~21600)\n", pres, grid, (double)h / (layers * reps));
+                   "(first-version FFMA2 tile GEMM: ~21600)\n", pres, grid, (double)h / (layers * reps));
         }
     printf("done\n");
     return 0;
