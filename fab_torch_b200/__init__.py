@@ -3,7 +3,7 @@ hot path behind the reference's own plugin API.  See DESIGN.md / INTEGRATION.md.
 from fab_torch_b200.point import Point
 from fab_torch_b200.types_ import Distribution, TrainableDistribution, TargetDistribution
 from fab_torch_b200.flow import B200RealNVP, make_wrapped_b200_realnvp
-from fab_torch_b200.targets import ManyWellEnergy, GMM, DiagGaussianTarget
+from fab_torch_b200.targets import ManyWellEnergy, GMM, DiagGaussianTarget, AldpSurrogateEnergy
 from fab_torch_b200.transition_operators import (TransitionOperator, HamiltonianMonteCarlo,
                                                   Metropolis, DeviceNoise, InjectedNoise,
                                                   make_gamma)

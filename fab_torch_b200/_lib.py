@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libfab_b200.so")
 
 FAB_TARGET_MANYWELL = 0
 FAB_TARGET_GMM = 1
+FAB_TARGET_ALDP_SURROGATE = 2
 FAB_MAX_UPDATES = 16
 
 

@@ -180,6 +180,9 @@ static bool target_ok(const fab_target_desc* t) {
     if (t->kind == FAB_TARGET_MANYWELL) return true;
     if (t->kind == FAB_TARGET_GMM)
         return t->n_mixes >= 1 && t->d_locs && t->d_scales && t->d_log_weights;
+    if (t->kind == FAB_TARGET_ALDP_SURROGATE)
+        return t->d_locs && t->d_scales && t->d_log_weights && (int)t->b >= 0 && (int)t->b < t->dim &&
+               (int)t->c >= 0 && (int)t->c < t->dim && (int)t->b != (int)t->c;
     return false;
 }
 

@@ -12,7 +12,8 @@ __global__ void k_target(fab_target_desc t, const float* __restrict__ x, float* 
     const float* xr = x + row * t.dim;
     float* gr = g ? g + row * t.dim : nullptr;
     float v = (t.kind == FAB_TARGET_MANYWELL) ? manywell_row(t, xr, gr, t.dim, lane)
-                                              : gmm_row(t, xr, gr, t.dim, lane);
+            : (t.kind == FAB_TARGET_ALDP_SURROGATE) ? aldp_row(t, xr, gr, t.dim, lane)
+                                                    : gmm_row(t, xr, gr, t.dim, lane);
     if (lane == 0) lp[row] = v;
 }
 

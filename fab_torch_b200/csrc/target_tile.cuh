@@ -74,6 +74,39 @@ __device__ __forceinline__ float gmm_row(const fab_target_desc& t, const float* 
     return lp - t.log_norm;
 }
 
+// ALDP surrogate (include/fab_b200.h): per-coordinate harmonic / periodic terms + one torsion
+// coupling; closed-form gradient.
+__device__ __forceinline__ float aldp_row(const fab_target_desc& t, const float* x, float* g, int d,
+                                          int lane) {
+    float e = 0.f;
+    const int ia = (int)t.b, ib = (int)t.c;
+    for (int j = lane; j < d; j += 32) {
+        const float v = x[j];
+        const float p0 = __ldg(t.d_scales + j), p1 = __ldg(t.d_locs + j), n = __ldg(t.d_log_weights + j);
+        float ej, gj;
+        if (n == 0.f) {
+            const float u = v - p1;
+            ej = 0.5f * p0 * u * u;
+            gj = -p0 * u;
+        } else {
+            float sn, cs;
+            sincosf(n * v - p1, &sn, &cs);
+            ej = p0 * (1.f - cs);
+            gj = -p0 * n * sn;
+        }
+        if (j == ia || j == ib) {
+            float sn, cs;
+            sincosf(x[ia] - x[ib], &sn, &cs);
+            if (j == ia) { ej += t.a * (1.f - cs); gj -= t.a * sn; }
+            else gj += t.a * sn;
+        }
+        e += ej;
+        if (g) g[j] = gj;
+    }
+    e = warp_sum(e);
+    return -e - t.log_norm;
+}
+
 // Evaluate the target for the T rows xs[T][ld]; lp_out[T] and gp[T][ld] (nullable) in shared.
 __device__ __forceinline__ void target_tile(const fab_target_desc& t, const float* xs, int ld,
                                             int d, int T, float* lp_out, float* gp) {
@@ -82,6 +115,8 @@ __device__ __forceinline__ void target_tile(const fab_target_desc& t, const floa
         float lp;
         if (t.kind == FAB_TARGET_MANYWELL)
             lp = manywell_row(t, xs + p * ld, gp ? gp + p * ld : nullptr, d, lane);
+        else if (t.kind == FAB_TARGET_ALDP_SURROGATE)
+            lp = aldp_row(t, xs + p * ld, gp ? gp + p * ld : nullptr, d, lane);
         else
             lp = gmm_row(t, xs + p * ld, gp ? gp + p * ld : nullptr, d, lane);
         if (lane == 0) lp_out[p] = lp;

@@ -145,3 +145,38 @@ class DiagGaussianTarget(GMM):
         if use_gpu and torch.cuda.is_available():
             self.cuda()
         self._cache = None
+
+
+class AldpSurrogateEnergy(_DeviceTarget):
+    """Closed-form 60-dof stand-in for the reference's OpenMM alanine-dipeptide density
+    (fab/target_distributions/aldp.py:17-159, BASELINE config 5): harmonic bond/angle-like
+    coordinates, periodic torsions with multiplicity 1..3 and one phi/psi-style coupling
+    (include/fab_b200.h: FAB_TARGET_ALDP_SURROGATE).  The tables are a pure function of
+    (dim, seed); `tables` may be passed to share them with another implementation."""
+
+    def __init__(self, dim: int = 60, seed: int = 0, tables=None, use_gpu: bool = True):
+        super().__init__()
+        if tables is None:
+            g = torch.Generator().manual_seed(1000 + seed)
+            tors = torch.arange(dim) % 3 == 2
+            mult = torch.where(tors, torch.randint(1, 4, (dim,), generator=g).float(), torch.zeros(dim))
+            p0 = torch.where(tors, 0.5 + 2.5 * torch.rand(dim, generator=g),
+                             1.0 + 24.0 * torch.rand(dim, generator=g))
+            p1 = torch.where(tors, (torch.rand(dim, generator=g) * 2 - 1) * math.pi,
+                             torch.rand(dim, generator=g) - 0.5)
+            idx = torch.nonzero(tors).flatten()
+            tables = dict(mult=mult, p0=p0, p1=p1, ia=int(idx[0]), ib=int(idx[1]), coupling=1.5)
+        self.dim = dim
+        self.register_buffer("mult", tables["mult"].float().contiguous())
+        self.register_buffer("p0", tables["p0"].float().contiguous())
+        self.register_buffer("p1", tables["p1"].float().contiguous())
+        self.ia, self.ib, self.coupling = int(tables["ia"]), int(tables["ib"]), float(tables["coupling"])
+        if use_gpu and torch.cuda.is_available():
+            self.cuda()
+
+    def target_desc(self, device=None):
+        if device is not None and self.p0.device != torch.device(device):
+            self.to(device)
+        return _lib.TargetDesc(_lib.FAB_TARGET_ALDP_SURROGATE, self.dim, 0, 0, self.coupling,
+                               float(self.ia), float(self.ib), 0.0, _lib.ptr(self.p1),
+                               _lib.ptr(self.p0), _lib.ptr(self.mult))

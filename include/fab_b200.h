@@ -34,6 +34,8 @@ extern "C" {
 
 #define FAB_TARGET_MANYWELL 0
 #define FAB_TARGET_GMM      1
+#define FAB_TARGET_ALDP_SURROGATE 2   /* BASELINE config 5: closed-form 60-dof stand-in for the
+                                         OpenMM alanine-dipeptide density (aldp.py:17-159)        */
 
 /* ---------------------------------------------------------------------------------------
  * Packed RealNVP parameters ("flow blob").
@@ -114,6 +116,11 @@ typedef struct fab_target_desc {
     const float* d_locs;      /* GMM [n_mixes, dim]                                      */
     const float* d_scales;    /* GMM [n_mixes, dim] diagonal of scale_tril               */
     const float* d_log_weights; /* GMM [n_mixes] log mixture weights (normalised)        */
+    /* ALDP surrogate: E(x) = sum_j e_j(x_j) + a * (1 - cos(x_ia - x_ib)),  ia = (int)b, ib = (int)c,
+     *   harmonic coordinate (d_log_weights[j] == 0): e_j = d_scales[j]/2 * (x_j - d_locs[j])^2
+     *   torsion  coordinate (multiplicity n = d_log_weights[j] > 0):
+     *                                               e_j = d_scales[j] * (1 - cos(n x_j - d_locs[j]))
+     * log_prob = -E(x) - log_norm; all three tables are [dim]. */
 } fab_target_desc;
 
 /* Interpolation gamma(x) = cq*log_q + cp*log_p and grad = gq_c*grad_log_q + gp_c*grad_log_p

@@ -104,6 +104,43 @@ class OracleDiagGaussian:
         return (self.dim,)
 
 
+def aldp_surrogate_tables(dim: int = 60, seed: int = 0):
+    """Parameters of the ALDP surrogate (BASELINE config 5; build-defined, the reference's
+    AldpBoltzmann -- fab/target_distributions/aldp.py:17-159 -- needs OpenMM and cannot run
+    here): every third coordinate is a torsion with multiplicity 1..3, the others are harmonic
+    (bond/angle-like, in the normalised internal coordinates the reference's flow works in); the
+    first two torsions are coupled like phi/psi.  A pure function of (dim, seed)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    tors = torch.arange(dim) % 3 == 2
+    mult = torch.where(tors, torch.randint(1, 4, (dim,), generator=g).float(), torch.zeros(dim))
+    p0 = torch.where(tors, 0.5 + 2.5 * torch.rand(dim, generator=g), 1.0 + 24.0 * torch.rand(dim, generator=g))
+    p1 = torch.where(tors, (torch.rand(dim, generator=g) * 2 - 1) * math.pi, torch.rand(dim, generator=g) - 0.5)
+    idx = torch.nonzero(tors).flatten()
+    return dict(mult=mult, p0=p0, p1=p1, ia=int(idx[0]), ib=int(idx[1]), coupling=1.5)
+
+
+class OracleAldpSurrogate:
+    """E(x) = sum_harmonic k/2 (x-m)^2 + sum_torsion A (1 - cos(n x - phi)) + C (1 - cos(x_ia - x_ib));
+    log_prob = -E.  Plain torch ops (autograd gives the gradient the kernel has in closed form)."""
+
+    def __init__(self, dim: int = 60, seed: int = 0, dtype=torch.float32):
+        t = aldp_surrogate_tables(dim, seed)
+        self.dim = dim
+        self.mult, self.p0, self.p1 = (t[k].to(dtype) for k in ("mult", "p0", "p1"))
+        self.ia, self.ib, self.coupling = t["ia"], t["ib"], t["coupling"]
+
+    def double(self):
+        self.mult, self.p0, self.p1 = self.mult.double(), self.p0.double(), self.p1.double()
+        return self
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        harm = 0.5 * self.p0 * (x - self.p1) ** 2
+        tors = self.p0 * (1 - torch.cos(self.mult * x - self.p1))
+        e = torch.where(self.mult == 0, harm, tors).sum(dim=1)
+        e = e + self.coupling * (1 - torch.cos(x[:, self.ia] - x[:, self.ib]))
+        return -e
+
+
 def to_double(target):
     """fp64 copy of an OracleGMM's tables (ground-truth runs)."""
     if isinstance(target, OracleGMM):

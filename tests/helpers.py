@@ -41,6 +41,16 @@ def make_gmm(dim, n_mixes, loc_scaling, log_var_scaling=0.1, seed=0, device="cud
     return to64, to, tp
 
 
+def make_aldp(dim=60, seed=0, device="cuda"):
+    """(oracle fp64, oracle fp32, product) ALDP-surrogate targets sharing the same tables."""
+    from oracle.targets import OracleAldpSurrogate, aldp_surrogate_tables
+    to = OracleAldpSurrogate(dim, seed)
+    to64 = OracleAldpSurrogate(dim, seed).double()
+    tp = fb.AldpSurrogateEnergy(dim, seed, tables=aldp_surrogate_tables(dim, seed),
+                                use_gpu=(device == "cuda"))
+    return to64, to, tp
+
+
 def rel_err(a, b):
     """max |a-b| / max(1, |b|) elementwise -> scalar (a: test value, b: truth)."""
     a = a.detach().double().cpu()

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import fab_torch_b200 as fb
-from helpers import make_flows, make_manywell, make_gmm, rel_err
+from helpers import make_flows, make_manywell, make_gmm, make_aldp, rel_err
 from oracle.noise import Float32RecordingNoise
 from oracle.sampler import OracleAIS, OracleHMC, OracleMetropolis
 
@@ -20,6 +20,8 @@ def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, 
     if tk == "mw":
         to, tp = make_manywell(dim)
         to32 = to
+    elif tk == "aldp":
+        to, to32, tp = make_aldp(dim)
     else:
         to, to32, tp = make_gmm(dim, 4, 8.0)
     if op_kind == "hmc":
@@ -64,8 +66,8 @@ AIS_CASES = [
     # BASELINE config 4 architecture (Many-Well-128, 10 layers x width 1280: the 8-slot tile
     # layout, 160 MB of weights streamed from HBM/L2), shortened chain
     dict(dim=128, K=10, npd=10, tk="mw", M=2, B=24, op_kind="hmc", epsilon=0.02, L=2, last_std=0.003),
-    # BASELINE config 5 shape (60-dof target, 20 distributions) on the many-well energy
-    dict(dim=60, K=4, npd=5, tk="mw", M=20, B=64, op_kind="hmc", epsilon=0.05, L=4),
+    # BASELINE config 5: 60-dof ALDP surrogate energy, 20 distributions, HMC L=4 (fab_buff.yaml:43)
+    dict(dim=60, K=4, npd=5, tk="aldp", M=20, B=64, op_kind="hmc", epsilon=0.05, L=4),
 ]
 
 

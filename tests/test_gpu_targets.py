@@ -1,7 +1,7 @@
 import pytest
 import torch
 
-from helpers import make_manywell, make_gmm, rel_err, assert_parity
+from helpers import make_manywell, make_gmm, make_aldp, rel_err, assert_parity
 import fab_torch_b200 as fb
 from oracle.targets import OracleDiagGaussian
 
@@ -51,3 +51,23 @@ def test_gmm_mask_and_gaussian_target():
     ref = OracleDiagGaussian(loc.double(), 1.0)
     x = torch.randn(100, 3)
     assert rel_err(tgt.log_prob(x.cuda()), ref.log_prob(x.double())) < 1e-5
+
+
+@pytest.mark.parametrize("dim", [60, 6])
+def test_aldp_surrogate(dim):
+    """BASELINE config 5 target: value and closed-form gradient vs the fp64 oracle (autograd); the
+    default tables (no `tables=`) must be the same pure function of (dim, seed)."""
+    to64, to, tp = make_aldp(dim)
+    assert torch.equal(fb.AldpSurrogateEnergy(dim, 0).p0.cpu(), tp.p0.cpu())
+    x = torch.randn(300, dim) * 1.5
+    x64 = x.double().requires_grad_(True)
+    ref = to64.log_prob(x64)
+    gref = torch.autograd.grad(ref.sum(), x64)[0]
+    x32 = x.clone().requires_grad_(True)
+    ref32 = to.log_prob(x32)
+    g32 = torch.autograd.grad(ref32.sum(), x32)[0]
+    xg = x.cuda().requires_grad_(True)
+    lp = tp.log_prob(xg)
+    g = torch.autograd.grad(lp.sum(), xg)[0]
+    assert_parity(lp, ref, ref32, "log_p")
+    assert_parity(g, gref, g32, "grad_log_p", floor=2e-5)
