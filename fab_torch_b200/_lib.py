@@ -96,6 +96,11 @@ SIGNATURES = {
     "fab_resample_workspace_bytes": (C.c_int64, [C.c_int64]),
     "fab_resample_systematic_u64": (C.c_int, [_P, C.c_int64, C.c_uint32, _P, _P, _P]),
     "fab_gather_rows_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "fab_buffer_add_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P,
+                                     C.c_int64, _P]),
+    "fab_buffer_topk_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "fab_buffer_topk_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "fab_buffer_adjust_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

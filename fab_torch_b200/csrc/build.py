@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ["fab_b200.cu"]
 HEADERS = ["common.cuh", "mma_gemm.cuh", "flow_tile.cuh", "target_tile.cuh", "tile_kernels.cuh",
-           "misc_kernels.cuh", os.path.join(ROOT, "include", "fab_b200.h")]
+           "misc_kernels.cuh", "buffer_kernels.cuh", os.path.join(ROOT, "include", "fab_b200.h")]
 OUT = os.path.join(HERE, "libfab_b200.so")
 
 

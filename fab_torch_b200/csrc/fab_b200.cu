@@ -7,6 +7,7 @@
 
 #include "tile_kernels.cuh"
 #include "misc_kernels.cuh"
+#include "buffer_kernels.cuh"
 
 namespace {
 
@@ -401,6 +402,56 @@ int fab_gather_rows_f32(const float* d_src, float* d_dst, const int64_t* d_anc, 
     k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_src, d_dst, (const long long*)d_anc, (long long)n, row_floats);
     CK_LAUNCH("k_gather_rows");
+    return FAB_OK;
+}
+
+int fab_buffer_add_f32(float* d_buf_x, float* d_buf_log_w, float* d_buf_log_q, int64_t max_length,
+                       int32_t dim, int64_t current_index, const float* d_x, const float* d_log_w,
+                       const float* d_log_q, int64_t batch, void* stream) {
+    if (!d_buf_x || !d_buf_log_w || !d_buf_log_q || max_length < 1 || dim < 1 || current_index < 0 ||
+        current_index >= max_length || batch < 0 || batch > max_length || (batch > 0 && (!d_x || !d_log_w || !d_log_q)))
+        return fail(FAB_E_INVALID, "fab_buffer_add_f32: bad arguments (batch <= max_length)");
+    if (batch == 0) return FAB_OK;
+    const long long tot = batch * dim;
+    unsigned grid = (unsigned)((tot + 255) / 256);
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_buffer_add<<<grid, 256, 0, (cudaStream_t)stream>>>(d_buf_x, d_buf_log_w, d_buf_log_q,
+                                                         (long long)max_length, dim,
+                                                         (long long)current_index, d_x, d_log_w,
+                                                         d_log_q, (long long)batch);
+    CK_LAUNCH("k_buffer_add");
+    return FAB_OK;
+}
+
+int64_t fab_buffer_topk_workspace_bytes(int64_t n) {
+    if (n < 0) return FAB_E_INVALID;
+    return n * 4 + 64;
+}
+
+int fab_buffer_topk_f32(const float* d_logits, const float* d_gumbel, int64_t n, int64_t k,
+                        int64_t* d_indices, void* d_workspace, void* stream) {
+    if (!d_logits || !d_gumbel || !d_indices || !d_workspace || n < 1 || k < 1 || k > n)
+        return fail(FAB_E_INVALID, "fab_buffer_topk_f32: need 1 <= k <= n");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned int* keys = (unsigned int*)d_workspace;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_buffer_keys<<<grid, 256, 0, s>>>(d_logits, d_gumbel, (long long)n, keys);
+    CK_LAUNCH("k_buffer_keys");
+    k_buffer_select<<<1, FAB_SEL_NT, 0, s>>>(keys, (long long)n, (long long)k, (long long*)d_indices);
+    CK_LAUNCH("k_buffer_select");
+    return FAB_OK;
+}
+
+int fab_buffer_adjust_f32(float* d_buf_log_w, float* d_buf_log_q, const int64_t* d_indices,
+                          const float* d_log_w_adjustment, const float* d_log_q, int64_t m,
+                          void* stream) {
+    if (!d_buf_log_w || !d_buf_log_q || m < 0 || (m > 0 && (!d_indices || !d_log_w_adjustment || !d_log_q)))
+        return fail(FAB_E_INVALID, "fab_buffer_adjust_f32: bad arguments");
+    if (m == 0) return FAB_OK;
+    k_buffer_adjust<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_buf_log_w, d_buf_log_q, (const long long*)d_indices, d_log_w_adjustment, d_log_q, (long long)m);
+    CK_LAUNCH("k_buffer_adjust");
     return FAB_OK;
 }
 

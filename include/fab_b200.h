@@ -269,6 +269,28 @@ int fab_resample_systematic_u64(const float* d_log_w, int64_t n, uint32_t u0, in
 int fab_gather_rows_f32(const float* d_src, float* d_dst, const int64_t* d_anc, int64_t n,
                         int32_t row_floats, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Prioritised replay buffer (fab/utils/prioritised_replay_buffer.py).
+ * The buffer lives in caller-owned device arrays x[max_length,dim], log_w[max_length],
+ * log_q_old[max_length].
+ * ------------------------------------------------------------------------------------- */
+/* add (:71-85): ring write of `batch` rows starting at current_index (batch <= max_length). */
+int fab_buffer_add_f32(float* d_buf_x, float* d_buf_log_w, float* d_buf_log_q, int64_t max_length,
+                       int32_t dim, int64_t current_index, const float* d_x, const float* d_log_w,
+                       const float* d_log_q, int64_t batch, void* stream);
+/* sample without replacement (:10-17, :88-100): indices of the k largest (gumbel[i] + logits[i]),
+ * i < n, written in ascending index order (the reference returns them in an unspecified order and
+ * then permutes them); exact radix select, ties towards the lower index, NaN above +inf like
+ * torch.topk.  d_gumbel = standard Gumbel noise drawn by the caller. */
+int64_t fab_buffer_topk_workspace_bytes(int64_t n);
+int fab_buffer_topk_f32(const float* d_logits, const float* d_gumbel, int64_t n, int64_t k,
+                        int64_t* d_indices, void* d_workspace, void* stream);
+/* adjust (:117-131): finite (adjustment, log_q) -> log_w[idx] += adjustment, log_q_old[idx] = log_q;
+ * otherwise log_w[idx] = -inf.  Indices must be unique (sampling without replacement). */
+int fab_buffer_adjust_f32(float* d_buf_log_w, float* d_buf_log_q, const int64_t* d_indices,
+                          const float* d_log_w_adjustment, const float* d_log_q, int64_t m,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
