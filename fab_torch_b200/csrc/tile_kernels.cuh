@@ -320,6 +320,7 @@ k_hmc_step(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
             s = warp_sum(s);
             if (lane == 0) ke0[p] = 0.5f * s;
         }
+        __syncthreads();        // the first leapfrog half-step below overwrites mom (racecheck)
         prof_mark(0);
         // leapfrog (hmc.py:138-147)
         for (int l = 0; l < a.L; ++l) {
