@@ -176,11 +176,17 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
         float* zn = zsel(L, cur ^ 1);
         float* h1 = b.h1;
         uint32_t* m1 = SAVE ? b.m1 + (size_t)k * L.MW : nullptr;
-        mma_gemm_wide<TP>(zsel(L, cur), L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mw1), NT1,
-                          lay + f.o_b1, [&](int nt, const float (&c)[4]) {
-                              if (nt < NTV) frag_store<TP>(zn, 8 * nt, g, t, c[0], c[1], c[2], c[3]);
-                              else hidden_fwd<TP, SAVE>(h1, m1, nt - NTV, g, t, c);
-                          });
+        auto epi1 = [&](int nt, const float (&c)[4]) {
+            if (nt < NTV) frag_store<TP>(zn, 8 * nt, g, t, c[0], c[1], c[2], c[3]);
+            else hidden_fwd<TP, SAVE>(h1, m1, nt - NTV, g, t, c);
+        };
+        // 41..48 tiles (config 2: 4 + 40): six per warp in ONE pass instead of a nearly empty second
+        if (NT1 > 8 * FAB_NTW && NT1 <= 8 * (FAB_NTW + 1))
+            mma_gemm_wide_n<TP, FAB_NTW + 1>(zsel(L, cur), L.D16 / 16,
+                                             reinterpret_cast<const float4*>(lay + f.o_mw1), NT1, lay + f.o_b1, epi1);
+        else
+            mma_gemm_wide<TP>(zsel(L, cur), L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mw1), NT1,
+                              lay + f.o_b1, epi1);
         mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false);
         __syncthreads();
         prof_mark(3);

@@ -98,10 +98,13 @@ __device__ __forceinline__ void load_a(const float* act, int kb, int g, int t, u
 // products of ONE k-tile go into a fresh accumulator, small terms first (they meet a near-empty
 // accumulator), and that 8-term partial sum is added to the running total with a round-to-nearest
 // FADD: one truncation per k-tile at partial-sum magnitude, with signs that average out.
-// FULL = every one of the NT_ tiles is live (no per-tile predicates around the MMAs).
-template <int TP, int NT_, bool FULL>
+// CNT > 0: exactly the first CNT tiles are live (compile time, no predicates around the MMAs);
+// CNT = 0: the first `cnt` tiles are live (run time, predicated).
+template <int TP, int NT_, int CNT>
 __device__ __forceinline__ void mma_pair(float (&c)[NT_][4], const float* act, int kb, int g, int t,
                                          const float4 (&w)[NT_], int cnt) {
+    constexpr bool FULL = CNT > 0;
+    constexpr int NL = CNT > 0 ? CNT : NT_;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         uint32_t ah[4], al[4];
@@ -109,19 +112,19 @@ __device__ __forceinline__ void mma_pair(float (&c)[NT_][4], const float* act, i
         uint32_t bh[NT_][2], bl[NT_][2];
         float cp[NT_][4];
 #pragma unroll
-        for (int i = 0; i < NT_; ++i) {
+        for (int i = 0; i < NL; ++i) {
             split_w(h == 0 ? w[i].x : w[i].z, bh[i][0], bl[i][0]);
             split_w(h == 0 ? w[i].y : w[i].w, bh[i][1], bl[i][1]);
             cp[i][0] = cp[i][1] = cp[i][2] = cp[i][3] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < NT_; ++i) if (FULL || i < cnt) mma_tf32(cp[i], al, bh[i][0], bh[i][1]);
+        for (int i = 0; i < NL; ++i) if (FULL || i < cnt) mma_tf32(cp[i], al, bh[i][0], bh[i][1]);
 #pragma unroll
-        for (int i = 0; i < NT_; ++i) if (FULL || i < cnt) mma_tf32(cp[i], ah, bl[i][0], bl[i][1]);
+        for (int i = 0; i < NL; ++i) if (FULL || i < cnt) mma_tf32(cp[i], ah, bl[i][0], bl[i][1]);
 #pragma unroll
-        for (int i = 0; i < NT_; ++i) if (FULL || i < cnt) mma_tf32(cp[i], ah, bh[i][0], bh[i][1]);
+        for (int i = 0; i < NL; ++i) if (FULL || i < cnt) mma_tf32(cp[i], ah, bh[i][0], bh[i][1]);
 #pragma unroll
-        for (int i = 0; i < NT_; ++i) {
+        for (int i = 0; i < NL; ++i) {
             c[i][0] += cp[i][0]; c[i][1] += cp[i][1]; c[i][2] += cp[i][2]; c[i][3] += cp[i][3];
         }
     }
@@ -149,22 +152,22 @@ __device__ __forceinline__ void mma_prefetch(const float4* __restrict__ Wf, int 
 // warp-uniformly once per owned tile with the lane's fragment: c[0],c[1] = (slot g, columns
 // 8nt+2t, +1), c[2],c[3] = (slot g+8, same columns).  The caller must __syncthreads() before the
 // operand `act` is overwritten and before anything the epilogue wrote is read.
-template <int TP, class Epi>
-__device__ __forceinline__ void mma_gemm_wide(const float* act, int KT2, const float4* __restrict__ Wf,
+template <int TP, int NTW, class Epi>
+__device__ __forceinline__ void mma_gemm_wide_n(const float* act, int KT2, const float4* __restrict__ Wf,
                                               int NT, const float* __restrict__ bias, Epi epi) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int npass = (NT + 8 * FAB_NTW - 1) / (8 * FAB_NTW);
+    const int npass = (NT + 8 * NTW - 1) / (8 * NTW);
     const int total = npass * KT2;
     // prefetch cursor (pass, kp) of the weight ring
     int pf_base = 0, pf_kp = 0, pf_it = 0;
-    auto fetch = [&](float4 (&dst)[FAB_NTW]) {
+    auto fetch = [&](float4 (&dst)[NTW]) {
         if (pf_it < total) {
             const float4* p = Wf + ((size_t)pf_kp * NT + pf_base + warp) * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < FAB_NTW; ++i)
+            for (int i = 0; i < NTW; ++i)
                 if (pf_base + warp + 8 * i < NT) dst[i] = ldg_stream(p + (size_t)i * 8 * 32);
             ++pf_it;
-            if (++pf_kp == KT2) { pf_kp = 0; pf_base += 8 * FAB_NTW; }
+            if (++pf_kp == KT2) { pf_kp = 0; pf_base += 8 * NTW; }
         }
     };
     // three-deep register ring: the main loop is unrolled by three so that no register moves are
@@ -172,17 +175,17 @@ __device__ __forceinline__ void mma_gemm_wide(const float* act, int KT2, const f
     // (profiles/microbench_mma_variants.cu times the alternatives in isolation -- two-deep ring,
     // packed f32x2 adds/splits, k-tile software pipelining, 16 warps: none beats this form in
     // the full kernel, where the deeper prefetch also covers the short GEMMs' L2 latency.)
-    float4 w0[FAB_NTW] = {}, w1[FAB_NTW] = {}, w2[FAB_NTW] = {};
+    float4 w0[NTW] = {}, w1[NTW] = {}, w2[NTW] = {};
     fetch(w0);
     fetch(w1);
     fetch(w2);
-    for (int base = 0; base < NT; base += 8 * FAB_NTW) {
+    for (int base = 0; base < NT; base += 8 * NTW) {
         int cnt = (NT - base - warp + 7) / 8;                 // tiles this warp owns in the pass
-        if (cnt > FAB_NTW) cnt = FAB_NTW;
+        if (cnt > NTW) cnt = NTW;
         if (cnt < 0) cnt = 0;
-        float c[FAB_NTW][4];
+        float c[NTW][4];
 #pragma unroll
-        for (int i = 0; i < FAB_NTW; ++i) {
+        for (int i = 0; i < NTW; ++i) {
             float b0 = 0.f, b1 = 0.f;
             if (bias && i < cnt) {
                 const float2 bv = *reinterpret_cast<const float2*>(bias + (base + warp + 8 * i) * 8 + 2 * t);
@@ -193,26 +196,29 @@ __device__ __forceinline__ void mma_gemm_wide(const float* act, int KT2, const f
             c[i][0] = b0; c[i][1] = b1; c[i][2] = b0; c[i][3] = b1;
         }
         int kp = 0;
-        if (cnt == FAB_NTW) {
-            for (; kp + 3 <= KT2; kp += 3) {
-                mma_pair<TP, FAB_NTW, true>(c, act, kp * 16, g, t, w0, cnt);
-                fetch(w0);
-                mma_pair<TP, FAB_NTW, true>(c, act, kp * 16 + 16, g, t, w1, cnt);
-                fetch(w1);
-                mma_pair<TP, FAB_NTW, true>(c, act, kp * 16 + 32, g, t, w2, cnt);
-                fetch(w2);
-            }
+#define FAB_RING3(CNT)                                                        \
+        for (; kp + 3 <= KT2; kp += 3) {                                       \
+            mma_pair<TP, NTW, CNT>(c, act, kp * 16, g, t, w0, cnt);            \
+            fetch(w0);                                                         \
+            mma_pair<TP, NTW, CNT>(c, act, kp * 16 + 16, g, t, w1, cnt);       \
+            fetch(w1);                                                         \
+            mma_pair<TP, NTW, CNT>(c, act, kp * 16 + 32, g, t, w2, cnt);       \
+            fetch(w2);                                                         \
         }
+        if (cnt == NTW) { FAB_RING3(NTW) }
+        else if (cnt == NTW - 1) { FAB_RING3(NTW - 1) }
+#undef FAB_RING3
         for (; kp < KT2; ++kp) {                 // tail / partially filled passes: rotate by moves
-            float4 w[FAB_NTW];
+            float4 w[NTW];
 #pragma unroll
-            for (int i = 0; i < FAB_NTW; ++i) { w[i] = w0[i]; w0[i] = w1[i]; w1[i] = w2[i]; }
+            for (int i = 0; i < NTW; ++i) { w[i] = w0[i]; w0[i] = w1[i]; w1[i] = w2[i]; }
             fetch(w2);
-            if (cnt == FAB_NTW) mma_pair<TP, FAB_NTW, true>(c, act, kp * 16, g, t, w, cnt);
-            else mma_pair<TP, FAB_NTW, false>(c, act, kp * 16, g, t, w, cnt);
+            if (cnt == NTW) mma_pair<TP, NTW, NTW>(c, act, kp * 16, g, t, w, cnt);
+            else if (cnt == NTW - 1) mma_pair<TP, NTW, NTW - 1>(c, act, kp * 16, g, t, w, cnt);
+            else mma_pair<TP, NTW, 0>(c, act, kp * 16, g, t, w, cnt);
         }
 #pragma unroll
-        for (int i = 0; i < FAB_NTW; ++i) {
+        for (int i = 0; i < NTW; ++i) {
             if (i < cnt) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) c[i][q] = fmaf(c[i][q], FAB_TRUNC_EPS, c[i][q]);
@@ -220,6 +226,13 @@ __device__ __forceinline__ void mma_gemm_wide(const float* act, int KT2, const f
             }
         }
     }
+}
+
+// default tile count per warp
+template <int TP, class Epi>
+__device__ __forceinline__ void mma_gemm_wide(const float* act, int KT2, const float4* __restrict__ Wf,
+                                              int NT, const float* __restrict__ bias, Epi epi) {
+    mma_gemm_wide_n<TP, FAB_NTW>(act, KT2, Wf, NT, bias, epi);
 }
 
 // k-split GEMM for narrow outputs.  Warp = ks*NGR + ngr owns n-tiles nt = base + ngr + NGR*i
@@ -267,8 +280,8 @@ __device__ __forceinline__ int mma_gemm_ksplit(const float* act, int KT2, const 
 #pragma unroll
             for (int i = 0; i < FAB_NTK; ++i) { w[i] = w0[i]; w0[i] = w1[i]; w1[i] = w2[i]; }
             fetch(w2);
-            if (cnt == FAB_NTK) mma_pair<TP, FAB_NTK, true>(c, act, (ks + j * KSe) * 16, g, t, w, cnt);
-            else mma_pair<TP, FAB_NTK, false>(c, act, (ks + j * KSe) * 16, g, t, w, cnt);
+            if (cnt == FAB_NTK) mma_pair<TP, FAB_NTK, FAB_NTK>(c, act, (ks + j * KSe) * 16, g, t, w, cnt);
+            else mma_pair<TP, FAB_NTK, 0>(c, act, (ks + j * KSe) * 16, g, t, w, cnt);
         }
 #pragma unroll
         for (int i = 0; i < FAB_NTK; ++i) {
