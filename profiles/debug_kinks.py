@@ -2,7 +2,7 @@
 For the worst particle of the flow test, perturb x by ~1e-6 in fp64 and see whether the fp64
 gradient itself jumps by a comparable amount."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from helpers import make_flows
