@@ -28,7 +28,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
            "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
     extra = os.environ.get("FAB_NVCC_FLAGS", "").split()
-    if extra:                      # experiment knobs, e.g. -DFAB_NT=512 -DFAB_PROF
+    if extra:                      # experiment knobs, e.g. -DFAB_PROF -DFAB_MIN_CTAS=2
         cmd[1:1] = extra
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -10,10 +10,9 @@
 #include <stdint.h>
 #include "fab_b200.h"
 
-#ifndef FAB_NT
-#define FAB_NT 256              // threads per tile CTA (256 or 512).  8 warps measured faster than 16:
-                                // the operand splits of the shared A fragments are repeated per warp
-#endif
+#define FAB_NT 256              // threads per tile CTA: 8 warps, fixed by the warp -> n-tile maps of
+                                // mma_gemm.cuh (16 warps were measured slower: the operand splits of
+                                // the shared A fragments are repeated per warp)
 #ifndef FAB_MIN_CTAS
 #define FAB_MIN_CTAS 1          // co-resident tile CTAs per SM the kernels are compiled for
 #endif

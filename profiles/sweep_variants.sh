@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build kernel variants on the GPU box and bench each (experiment helper).
-# usage: sweep_variants.sh "<nvcc -D flags>[;ENV=VAL ...]" ...   e.g. "-DFAB_NT=512" "-DFAB_MIN_CTAS=2;FAB_FORCE_TILE=8"
+# usage: sweep_variants.sh "<nvcc -D flags>[;ENV=VAL ...]" ...   e.g. "-DFAB_PROF" "-DFAB_MIN_CTAS=2;FAB_FORCE_TILE=8"
 mkdir -p gpurun_out
 for spec in "$@"; do
   v="${spec%%;*}"; envs=""; [[ "$spec" == *";"* ]] && envs="${spec#*;}"
