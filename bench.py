@@ -233,7 +233,7 @@ def build_gpu(cfg, device, group):
                                   epsilon=cfg["epsilon"], n_outer=cfg["n_outer"], L=cfg["L"]).to(device)
     ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=cfg["p_target"],
                                        alpha=cfg["alpha"], n_intermediate_distributions=cfg["M"],
-                                       process_group=group)
+                                       process_group=group, use_cuda_graph=group is None)
     return flow, target, op, ais
 
 
@@ -293,11 +293,7 @@ def run_gpu_arm(args):
     d2h = (h_x.numel() + h_w.numel()) * 4 + 40
 
     def e2e_step():
-        d_eps = h_eps.to(device, non_blocking=True)
-        d_mom = h_mom.to(device, non_blocking=True)
-        d_exp = h_exp.to(device, non_blocking=True)
-        flow._eps_override = d_eps
-        op.chain_noise_override = [(d_mom[j], d_exp[j]) for j in range(M)]
+        ais.set_next_noise(h_eps, h_mom, h_exp)          # pinned host -> device inside the call
         pt, lw = ais.sample_and_log_weights(B_global)
         n = lw.shape[0]
         h_x[:n].copy_(pt.x, non_blocking=True)
@@ -358,7 +354,7 @@ def run_gpu_arm(args):
                     warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=WORKLOAD, global_batch=B_global, l2_flush_between_steps=True,
-                                tuner="on", **{k: cfg[k] for k in ("dim", "n_layers", "M", "L", "n_outer")}),
+                                tuner="on", cuda_graph=bool(ais.use_cuda_graph and world == 1), **{k: cfg[k] for k in ("dim", "n_layers", "M", "L", "n_outer")}),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d * world,
                              d2h_bytes_per_step=d2h * world, ms_per_step=total_e2e_ms / args.steps),
                     gpu_launches=launches_per_step * args.steps, clocks=clock_rec, roofline=roof,

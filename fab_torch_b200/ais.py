@@ -54,7 +54,7 @@ class AnnealedImportanceSampler:
                  p_target: bool, alpha: Optional[float] = None,
                  n_intermediate_distributions: int = 1,
                  distribution_spacing_type: str = "linear",
-                 process_group=None):
+                 process_group=None, use_cuda_graph: bool = False):
         if not p_target:
             assert alpha is not None, "Must specify alpha if AIS target is not p."
         self.base_distribution = base_distribution
@@ -76,6 +76,14 @@ class AnnealedImportanceSampler:
         self._target = target
         self._host = None      # pinned read-back record
         self._filter_ws = None
+        # use_cuda_graph: capture the whole chain (init, filters, M transitions, ESS) once per
+        # (batch, mode) and replay it -- removes the per-kernel launch cost that dominates small
+        # configurations (BASELINE config 1: 27 launches for ~0.3 ms of device work).  Single-GPU
+        # only; the noise lives in persistent buffers that are refilled before every replay.
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self._graph_warm = set()
+        self._next_noise = None
 
     # ------------------------------------------------------------------------------------------
     def get_logging_info(self) -> Dict[str, Any]:
@@ -120,20 +128,22 @@ class AnnealedImportanceSampler:
         return (make_gamma(self.B_space[j], self.alpha, self.p_target),
                 make_gamma(self.B_space[j + 1], self.alpha, self.p_target))
 
-    def _run_chain(self, batch_size: int, logging: bool, timings=None):
-        """Enqueue the whole chain; returns device tensors + the device record (no sync)."""
+    def _run_chain(self, batch_size: int, logging: bool, timings=None, noise=None):
+        """Enqueue the whole chain; returns device tensors + the device record (no sync).
+        `noise` = (base eps [n,d], per-transition noise pairs) replaces the draws."""
         flow, op, target = self.base_distribution, self.transition_operator, self._target
         dev = flow._device()
         L = _lib.lib()
         d = flow.dim
         n = batch_size
         with_grad = bool(op.uses_grad_info)
-        noise = op.noise
-        eps = getattr(flow, "_eps_override", None)
-        if eps is not None:
+        eps = noise[0] if noise is not None else getattr(flow, "_eps_override", None)
+        if noise is not None:
+            pass
+        elif eps is not None:
             flow._eps_override = None
         else:
-            eps = noise.base_eps(n, d, dev)
+            eps = op.noise.base_eps(n, d, dev)
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         pt = Point(f(n, d), f(n), f(n), f(n, d) if with_grad else None,
                    f(n, d) if with_grad else None)
@@ -151,7 +161,7 @@ class AnnealedImportanceSampler:
         if logging:
             self._ess(pt.log_p, pt.log_q, counts[0:1], rec[0:3])   # ESS over base weights
         M = self.n_intermediate_distributions
-        chain_noise = op.chain_noise(M, n, d, dev)
+        chain_noise = noise[1] if noise is not None else op.chain_noise(M, n, d, dev)
         for j in range(1, M + 1):
             if timings is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -165,6 +175,58 @@ class AnnealedImportanceSampler:
         if logging:
             self._ess(log_w, None, counts[1:2], rec[3:6])
         return pt, log_w, counts, rec
+
+    def set_next_noise(self, eps: torch.Tensor, noise_a: torch.Tensor, noise_b: torch.Tensor):
+        """Pre-drawn randomness for the NEXT `sample_and_log_weights` call, e.g. pinned host
+        tensors (copied host->device inside the call): eps [n,d]; HMC: momentum [M,n_outer,n,d] +
+        exponential [M,n_outer,n]; Metropolis: proposal [M,n_updates,n,d] + uniform [M,n_updates,n]."""
+        self._next_noise = (eps, noise_a, noise_b)
+
+    def _run_graphed(self, local: int, logging: bool):
+        """Chain through a captured CUDA graph: first call with a given key runs eagerly (warm-up:
+        workspaces, weight blob, kernel attributes), the second captures, later ones replay."""
+        flow, op = self.base_distribution, self.transition_operator
+        dev = flow._device()
+        d, M = flow.dim, self.n_intermediate_distributions
+        blob = flow.blob()                                   # repacked in place if parameters changed
+        key = (local, logging, self.p_target, self.alpha, op.p_target, op.alpha,
+               bool(getattr(op, "eval_mode", False)), getattr(op, "adjust_step_size", None),
+               blob.data_ptr(), id(op), str(dev))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = dict(eps=torch.empty(local, d, dtype=torch.float32, device=dev),
+                       noise=op.chain_noise_static(M, local, d, dev), graph=None)
+            self._graphs[key] = ent
+        # this call's randomness -> the persistent buffers (same generator calls as the eager path)
+        if self._next_noise is not None:
+            (e, a, b), self._next_noise = self._next_noise, None
+            ent["eps"].copy_(e, non_blocking=True)
+            ent["noise"][0].copy_(a, non_blocking=True)
+            ent["noise"][1].copy_(b, non_blocking=True)
+        else:
+            eps = getattr(flow, "_eps_override", None)
+            if eps is not None:
+                flow._eps_override = None
+                ent["eps"].copy_(eps)
+            elif type(op.noise).__name__ != "DeviceNoise":
+                ent["eps"].copy_(op.noise.base_eps(local, d, dev))
+            else:
+                ent["eps"].normal_()
+            op.fill_chain_noise(ent["noise"])
+        pairs = [(ent["noise"][0][j], ent["noise"][1][j]) for j in range(M)]
+        if key not in self._graph_warm:
+            self._graph_warm.add(key)
+            return self._run_chain(local, logging, noise=(ent["eps"], pairs))
+        if ent["graph"] is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pt, log_w, counts, rec = self._run_chain(local, logging, noise=(ent["eps"], pairs))
+            ent.update(graph=g, out=(pt, log_w, counts, rec))
+        ent["graph"].replay()
+        pt, log_w, counts, rec = ent["out"]
+        c = lambda t: None if t is None else t.clone()
+        return (Point(c(pt.x), c(pt.log_q), c(pt.log_p), c(pt.grad_log_q), c(pt.grad_log_p)),
+                log_w.clone(), counts, rec)
 
     def time_transitions(self, batch_size: int, repeats: int = 1) -> float:
         """Mean device time (ms) of one fused transition launch, measured with CUDA events on the
@@ -187,7 +249,18 @@ class AnnealedImportanceSampler:
         op = self.transition_operator
         op.process_group = self.process_group
         local = fdist.shard_size(batch_size, self.process_group)
-        pt, log_w, counts, rec = self._run_chain(local, logging)
+        if self.use_cuda_graph and self.process_group is None:
+            pt, log_w, counts, rec = self._run_graphed(local, logging)
+        else:
+            if self._next_noise is not None:
+                (e, a, b), self._next_noise = self._next_noise, None
+                dev_ = self.base_distribution._device()
+                a, b = a.to(dev_, non_blocking=True), b.to(dev_, non_blocking=True)
+                pt, log_w, counts, rec = self._run_chain(
+                    local, logging, noise=(e.to(dev_, non_blocking=True),
+                                           [(a[j], b[j]) for j in range(a.shape[0])]))
+            else:
+                pt, log_w, counts, rec = self._run_chain(local, logging)
         dev = log_w.device
         if self._host is None:
             self._host = torch.empty(10, dtype=torch.float32).pin_memory()

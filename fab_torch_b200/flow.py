@@ -173,7 +173,12 @@ class B200RealNVP(TrainableDistribution):
         key = self._param_key()
         if self._blob is None or key != self._blob_key:
             with torch.no_grad():
-                self._blob = self._pack()
+                new = self._pack()
+                if self._blob is not None and self._blob.shape == new.shape and \
+                        self._blob.device == new.device:
+                    self._blob.copy_(new)      # same storage: captured CUDA graphs stay valid
+                else:
+                    self._blob = new
             self._blob_key = key
         return self._blob
 

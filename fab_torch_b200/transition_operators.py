@@ -277,6 +277,22 @@ class HamiltonianMonteCarlo(TransitionOperator):
         return [(self.noise.momentum(j + 1, self.n_outer, n, d, dev),
                  self.noise.exponential(j + 1, self.n_outer, n, dev)) for j in range(M)]
 
+    def chain_noise_static(self, M: int, n: int, d: int, dev):
+        """Persistent noise buffers for a CUDA-graph-captured chain (ais.py: use_cuda_graph)."""
+        return (torch.empty((M, self.n_outer, n, d), dtype=torch.float32, device=dev),
+                torch.empty((M, self.n_outer, n), dtype=torch.float32, device=dev))
+
+    def fill_chain_noise(self, static) -> None:
+        """Refill the static buffers: injected / overridden noise is copied in, the default device
+        RNG draws in place (same generator calls, in the same order, as `chain_noise`)."""
+        a, b = static
+        if self.chain_noise_override is not None or type(self.noise) is not DeviceNoise:
+            for j, (x, y) in enumerate(self.chain_noise(a.shape[0], a.shape[2], a.shape[3], a.device)):
+                a[j].copy_(x); b[j].copy_(y)
+        else:
+            a.normal_()
+            b.exponential_(1.0)
+
     def run(self, point: Point, i: int, beta, log_w: Optional[torch.Tensor] = None,
             w_update=None, n_active: Optional[torch.Tensor] = None, noise=None) -> Point:
         """One HMC transition at distribution i.  `w_update=(g_w, g_next)` (the sampler's gammas at
@@ -373,6 +389,19 @@ class Metropolis(TransitionOperator):
             return [(prop[j], unif[j]) for j in range(M)]
         return [(self.noise.proposal(j + 1, self.n_updates, n, d, dev),
                  self.noise.uniform(j + 1, self.n_updates, n, dev)) for j in range(M)]
+
+    def chain_noise_static(self, M: int, n: int, d: int, dev):
+        return (torch.empty((M, self.n_updates, n, d), dtype=torch.float32, device=dev),
+                torch.empty((M, self.n_updates, n), dtype=torch.float32, device=dev))
+
+    def fill_chain_noise(self, static) -> None:
+        a, b = static
+        if self.chain_noise_override is not None or type(self.noise) is not DeviceNoise:
+            for j, (x, y) in enumerate(self.chain_noise(a.shape[0], a.shape[2], a.shape[3], a.device)):
+                a[j].copy_(x); b[j].copy_(y)
+        else:
+            a.normal_()
+            b.uniform_()
 
     def run(self, point: Point, i: int, beta, log_w: Optional[torch.Tensor] = None,
             w_update=None, n_active: Optional[torch.Tensor] = None, noise=None) -> Point:

@@ -49,7 +49,7 @@ def c1():
     op = fb.Metropolis(8, 2, flow.log_prob, target.log_prob, n_updates=1, alpha=2.0, p_target=False,
                        max_step_size=5.0, min_step_size=5.0, adjust_step_size=False).to(dev)
     ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=False, alpha=2.0,
-                                       n_intermediate_distributions=8)
+                                       n_intermediate_distributions=8, use_cuda_graph=True)
     ms = timed(lambda: ais.sample_and_log_weights(512), 5, 50)
     out = dict(config="C1 gmm40_d2_realnvp4x80_M8_metropolis_b512", ms_per_call=ms, particles_per_s=512 / ms * 1e3)
     try:
@@ -102,7 +102,7 @@ def c5():
     op = fb.HamiltonianMonteCarlo(M, dim, flow.log_prob, target.log_prob, alpha=2.0, p_target=False,
                                   epsilon=0.1, n_outer=1, L=4).to(dev)
     ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=False, alpha=2.0,
-                                       n_intermediate_distributions=M)
+                                       n_intermediate_distributions=M, use_cuda_graph=True)
 
     def sampler():
         pt, lw = ais.sample_and_log_weights(B, logging=False)

@@ -175,3 +175,56 @@ def test_all_invalid_raises():
                                        n_intermediate_distributions=2)
     with pytest.raises(Exception, match="No valid points generated in sampling the chain init"):
         ais.sample_and_log_weights(64)
+
+
+@pytest.mark.parametrize("op_kind", ["hmc", "metropolis"])
+def test_cuda_graph_chain_equals_eager(op_kind):
+    """use_cuda_graph=True (warm-up call, capture, replays) must reproduce the eager chain bit for
+    bit on the same seed -- including after a parameter update (the weight blob is repacked in
+    place, the captured graph stays valid) and after set_ais_target-style p_target flips."""
+    dim, K, npd, M, B = (32, 4, 6, 5, 300) if op_kind == "hmc" else (2, 4, 40, 8, 512)
+
+    def build(graph):
+        _, _, fp = make_flows(dim, K, npd, last_std=0.02)
+        if op_kind == "hmc":
+            _, tp = make_manywell(dim)
+            op = fb.HamiltonianMonteCarlo(M, dim, fp.log_prob, tp.log_prob, alpha=2.0, p_target=False,
+                                          epsilon=0.1, L=3, n_outer=2).cuda()
+        else:
+            _, _, tp = make_gmm(dim, 4, 8.0)
+            op = fb.Metropolis(M, dim, fp.log_prob, tp.log_prob, n_updates=2, alpha=2.0, p_target=False,
+                               max_step_size=1.0, min_step_size=0.5).cuda()
+        ais = fb.AnnealedImportanceSampler(fp, tp.log_prob, op, p_target=False, alpha=2.0,
+                                           n_intermediate_distributions=M, use_cuda_graph=graph)
+        return fp, op, ais
+
+    (f_e, op_e, ais_e), (f_g, op_g, ais_g) = build(False), build(True)
+    for step in range(5):
+        if step == 3:            # "optimiser step": same parameter update on both sides
+            with torch.no_grad():
+                for f in (f_e, f_g):
+                    f._nf_model.q0.loc.add_(0.05)
+                    f._nf_model.flows[0].linears[2].weight.mul_(1.1)
+        if step == 4:            # FABModel.set_ais_target(min_is_target=False)
+            for a, o in ((ais_e, op_e), (ais_g, op_g)):
+                a.p_target = o.p_target = True
+        outs = []
+        for ais in (ais_e, ais_g):
+            torch.manual_seed(100 + step)
+            outs.append(ais.sample_and_log_weights(B))
+        (pt_e, lw_e), (pt_g, lw_g) = outs
+        assert torch.equal(lw_e, lw_g) and torch.equal(pt_e.x, pt_g.x) and torch.equal(pt_e.log_q, pt_g.log_q)
+        assert ais_e.get_logging_info() == ais_g.get_logging_info()
+    assert any(e["graph"] is not None for e in ais_g._graphs.values())
+    # pre-drawn host noise goes straight into the graph's persistent buffers
+    g = torch.Generator().manual_seed(9)
+    n2 = op_e.n_outer if op_kind == "hmc" else op_e.n_updates
+    eps = torch.randn(B, dim, generator=g).pin_memory()
+    a = torch.randn(M, n2, B, dim, generator=g).pin_memory()
+    b = (torch.empty(M, n2, B).exponential_(1.0, generator=g) if op_kind == "hmc"
+         else torch.rand(M, n2, B, generator=g)).pin_memory()
+    outs = []
+    for ais in (ais_e, ais_g):
+        ais.set_next_noise(eps, a, b)
+        outs.append(ais.sample_and_log_weights(B))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0].x, outs[1][0].x)
