@@ -11,7 +11,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfab_b200.so")
+# FAB_B200_LIB: experiment hook (A/B runs of two builds inside one GPU call, profiles/)
+LIB_PATH = os.environ.get("FAB_B200_LIB") or os.path.join(_HERE, "csrc", "libfab_b200.so")
 
 FAB_TARGET_MANYWELL = 0
 FAB_TARGET_GMM = 1

@@ -63,8 +63,8 @@ struct TileLayout {
     int o_zs0, o_zs1, o_gs, o_par, o_h1, o_h2, o_red;
     int o_sy2, o_ses, o_m1, o_m2;       // saved-for-backward, [K][...]
     int o_ld;                           // [TP] running log-det
-    int o_scl;                          // [FAB_NWARPS][TP] per-warp partial sums of the scales
-    int o_const;                        // loc[DP], log_scale[DP], 1/scale[DP], logs[K]
+    int o_scl;                          // [DP + d2][TP] per-(row, slot) terms of the per-particle sums
+    int o_const;                        // loc[DP], log_scale[DP], 1/scale[DP], logs[K], sum(logs)
     int o_state;                        // kernel-specific state area
     int total_floats;
 };
@@ -116,8 +116,8 @@ __host__ inline TileLayout make_tile_layout(const fab_flow_desc& f, int T, int T
     L.o_m1 = take(KSV * L.MW);
     L.o_m2 = take(KSV * L.MW);
     L.o_ld = take(TP);
-    L.o_scl = take(FAB_NWARPS * TP);
-    L.o_const = take(3 * L.DP + L.K);
+    L.o_scl = take((L.DP + L.d2) * TP);
+    L.o_const = take(3 * L.DP + L.K + 1);
     L.o_state = take(state_floats);
     L.total_floats = o;
     return L;

@@ -65,6 +65,12 @@ __device__ __forceinline__ void tile_init(const TileLayout& L, const fab_flow_de
     }
     for (int k = threadIdx.x; k < L.K; k += FAB_NT)
         b.logs[k] = __ldg(blob + f.off_layers + (size_t)k * f.layer_stride + f.o_logs);
+    if (threadIdx.x == 0) {                      // sum_k sum(log_S_k), added to every log-det at once
+        float tot = 0.f;
+        for (int k = 0; k < L.K; ++k)
+            tot += __ldg(blob + f.off_layers + (size_t)k * f.layer_stride + f.o_logs);
+        b.logs[L.K] = tot;
+    }
     __syncthreads();
 }
 
@@ -138,25 +144,28 @@ __device__ __forceinline__ int mlp_tail(const TileLayout& L, const float* __rest
     return KSe;
 }
 
-// ld[p] += add - sum_w scl[w][p]   (threads < TP; scl holds the per-warp partial scale sums)
+// Per-particle sums over a row index j in a CANONICAL order.  The log-density of a particle is
+//   -d/2 log 2pi - sum_j gauss_j - sum_j (sum_layers scale_kj) + sum_k sum(log_S_k):
+// rows [0, d) of scl hold the Gaussian terms, rows [d, d + d2) the coupling scales ACCUMULATED
+// over the layers by the thread that owns (j, slot) in every layer (no per-layer reduction);
+// one reduction at the end: half-warp (2*warp + lane/16) owns particle p, lane j%16 adds its
+// rows in order, a fixed xor tree joins the 16 lanes.  The order depends neither on the thread
+// mapping of the producers nor on the tile configuration, so a particle's result does not depend
+// on the batch it is evaluated in (sharded == single-device runs bit for bit,
+// tests/multi_gpu_check.py).  Returns the sum in every lane of the half-warp; `p` is that
+// half-warp's particle (may be >= TP).
 template <int TP>
-__device__ __forceinline__ void logdet_accumulate(const TileBufs& b, float add) {
-    if (threadIdx.x < TP) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < FAB_NWARPS; ++w) s += b.scl[w * TP + threadIdx.x];
-        b.ld[threadIdx.x] += add - s;
-    }
-}
-
-// sum a per-thread value over the threads that share slot p = tid % TP inside a warp and deposit
-// it in scl[warp][p]
-template <int TP>
-__device__ __forceinline__ void slot_partial(const TileBufs& b, float v) {
-    v += __shfl_xor_sync(FAB_FULL, v, 16);
-    if (TP == 8) v += __shfl_xor_sync(FAB_FULL, v, 8);
+__device__ __noinline__ float slot_column_sum(const float* scl, int nj, int& p) {
     const int lane = threadIdx.x & 31;
-    if (lane < TP) b.scl[(threadIdx.x >> 5) * TP + lane] = v;
+    p = 2 * (threadIdx.x >> 5) + (lane >> 4);
+    float s = 0.f;
+    if (p < TP)
+        for (int j = lane & 15; j < nj; j += 16) s += scl[j * TP + p];
+    s += __shfl_xor_sync(FAB_FULL, s, 8);
+    s += __shfl_xor_sync(FAB_FULL, s, 4);
+    s += __shfl_xor_sync(FAB_FULL, s, 2);
+    s += __shfl_xor_sync(FAB_FULL, s, 1);
+    return s;
 }
 
 // x in zsel(L, cur) -> z in zsel(L, cur') (cur' returned), log q in lq_out[p] (shared, p < TP).  With
@@ -168,7 +177,8 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
     const TileBufs b = tile_bufs(L);
     constexpr int S = ActL<TP>::S;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    if (threadIdx.x < TP) b.ld[threadIdx.x] = 0.f;
+    float* sacc = b.scl + (size_t)L.d * TP;                 // accumulated scales, rows [d, d + d2)
+    for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) sacc[e] = 0.f;   // (each e has one owner)
     const int NT1 = L.D8 / 8 + L.NTH, NTV = L.D8 / 8;
     for (int k = L.K - 1; k >= 0; --k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
@@ -195,7 +205,6 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
         // coupling inverse: y2 = (v2 - shift) * exp(-scale)
         {
             const float* b3 = lay + f.o_b3;
-            float ssum = 0.f;
             for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) {
                 const int j = e / TP, p = e - j * TP;
                 const float shift = red_sum<TP>(b.red, KSe, L.P8, p, j) + __ldg(b3 + j);
@@ -204,39 +213,33 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
                 float* zp = zn + (size_t)(L.d1 + j) * S + p;
                 const float y2 = (*zp - shift) * es;
                 *zp = y2;
-                ssum += scale;
+                sacc[e] += scale;
                 if (SAVE) {
                     b.sy2[((size_t)k * L.d2 + j) * TP + p] = y2;
                     b.ses[((size_t)k * L.d2 + j) * TP + p] = es;
                 }
             }
-            slot_partial<TP>(b, ssum);
         }
         __syncthreads();
-        logdet_accumulate<TP>(b, b.logs[k]);
         prof_mark(8);
         cur ^= 1;
-        // (scl / ld are next touched after at least two more barriers)
     }
-    __syncthreads();
     // base Gaussian: log N(z; loc, exp(log_scale)) and its z-gradient
     {
         const float* z = zsel(L, cur);
-        float s = 0.f;
         for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
             const int j = e / TP, p = e - j * TP;
             const float inv = b.inv[j];
             const float u = (z[(size_t)j * S + p] - b.loc[j]) * inv;
-            s += b.lsc[j] + 0.5f * u * u;
+            b.scl[e] = b.lsc[j] + 0.5f * u * u;
             if (SAVE) b.gs[(size_t)j * S + p] = -u * inv;
         }
-        slot_partial<TP>(b, s);
         __syncthreads();
-        if (threadIdx.x < TP) {
-            float tot = 0.f;
-#pragma unroll
-            for (int w = 0; w < FAB_NWARPS; ++w) tot += b.scl[w * TP + threadIdx.x];
-            lq_out[threadIdx.x] = b.ld[threadIdx.x] + (-0.5f * (float)L.d * 1.8378770664093453f - tot);
+        {
+            int p;
+            const float tot = slot_column_sum<TP>(b.scl, L.d + L.d2, p);
+            if ((threadIdx.x & 15) == 0 && p < TP)
+                lq_out[p] = b.logs[L.K] + (-0.5f * (float)L.d * 1.8378770664093453f - tot);
         }
     }
     __syncthreads();
@@ -321,24 +324,17 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     float* z = zsel(L, cur);
     {   // base: z = loc + exp(log_scale)*eps ; log p0 = -d/2 log 2pi - sum(log_scale + eps^2/2)
-        float s = 0.f;
         for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
             const int j = e / TP, p = e - j * TP;
             const float ls = b.lsc[j];
             const float ev = z[(size_t)j * S + p];
-            s += ls + 0.5f * ev * ev;
+            b.scl[e] = ls + 0.5f * ev * ev;
             z[(size_t)j * S + p] = b.loc[j] + expf(ls) * ev;
-        }
-        slot_partial<TP>(b, s);
-        __syncthreads();
-        if (threadIdx.x < TP) {
-            float tot = 0.f;
-#pragma unroll
-            for (int w = 0; w < FAB_NWARPS; ++w) tot += b.scl[w * TP + threadIdx.x];
-            b.ld[threadIdx.x] = -0.5f * (float)L.d * 1.8378770664093453f - tot;
         }
         __syncthreads();
     }
+    float* sacc = b.scl + (size_t)L.d * TP;                 // accumulated scales, rows [d, d + d2)
+    for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) sacc[e] = 0.f;
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
         // h1 = relu(z1 @ W1^T + b1): rows >= d1 of the operand meet zero weight rows
@@ -354,20 +350,16 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
         const int KSe = mlp_tail<TP, false>(L, lay, f, k, lay + f.o_mix_inv, L.D8 / 8, true);
         {
             const float* b3 = lay + f.o_b3;
-            float ssum = 0.f;
             for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) {
                 const int j = e / TP, p = e - j * TP;
                 const float shift = red_sum<TP>(b.red, KSe, L.P8, p, j) + __ldg(b3 + j);
                 const float scale = red_sum<TP>(b.red, KSe, L.P8, p, L.d2 + j) + __ldg(b3 + L.d2 + j);
                 float* zp = z + (size_t)(L.d1 + j) * S + p;
                 *zp = *zp * expf(scale) + shift;
-                ssum += scale;
+                sacc[e] += scale;               // log q -= sum(scale) - sum(log_S), reduced at the end
             }
-            slot_partial<TP>(b, ssum);
         }
         __syncthreads();
-        // log q -= sum(scale);  log q -= (-sum log_S)
-        logdet_accumulate<TP>(b, b.logs[k]);
         // u' = [v1,y2] @ Wmix^-1
         const int KS2 = mma_gemm_ksplit<TP>(z, L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mix_inv),
                                             L.D8 / 8, b.red);
@@ -380,6 +372,11 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
         }
         __syncthreads();
     }
-    if (threadIdx.x < TP) lq_out[threadIdx.x] = b.ld[threadIdx.x];
+    {
+        int p;
+        const float tot = slot_column_sum<TP>(b.scl, L.d + L.d2, p);
+        if ((threadIdx.x & 15) == 0 && p < TP)
+            lq_out[p] = b.logs[L.K] + (-0.5f * (float)L.d * 1.8378770664093453f - tot);
+    }
     __syncthreads();
 }

@@ -10,12 +10,6 @@ and states identical, ESS / log Z / tuner state equal to rounding of the reducti
 import os
 import sys
 
-# Same particles-per-CTA on the sharded and the single-device run: per-particle results do not
-# depend on the other particles of a tile, but the log-det / Gaussian reductions associate
-# differently in the 8-slot and the 16-slot tile layout, so bit-for-bit equality is a statement
-# about equal tile configurations (across configurations the agreement is to fp32 rounding).
-os.environ.setdefault("FAB_FORCE_TILE", "4")
-
 import torch
 import torch.distributed as dist
 
