@@ -335,6 +335,7 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
     }
     float* sacc = b.scl + (size_t)L.d * TP;                 // accumulated scales, rows [d, d + d2)
     for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) sacc[e] = 0.f;
+    __syncthreads();            // (a flow without coupling layers goes straight to the final sum)
     for (int k = 0; k < L.K; ++k) {
         const float* lay = blob + f.off_layers + (size_t)k * f.layer_stride;
         // h1 = relu(z1 @ W1^T + b1): rows >= d1 of the operand meet zero weight rows
