@@ -1,5 +1,6 @@
 // libfab_b200.so -- C ABI (include/fab_b200.h) over the sm_100a kernels.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,8 @@ int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t _e = cudaGetLastError();                        \
         if (_e != cudaSuccess) return cuda_fail(_e, what);          \
     } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kMaxSmemBytes = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
@@ -192,6 +195,20 @@ int fab_target_logprob_grad_f32(const fab_target_desc* target, const float* d_x,
     if (!target_ok(target) || !d_x || !d_log_p || n < 0)
         return fail(FAB_E_INVALID, "fab_target_logprob_grad_f32: bad arguments");
     if (n == 0) return FAB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (target->kind == FAB_TARGET_MANYWELL && aligned16(d_x) && (!d_grad || aligned16(d_grad)) &&
+        (target->dim == 32 || target->dim == 64 || target->dim == 128)) {
+        // streaming form: rows of 8*C float4s, 4 rows per thread in flight
+        constexpr int U = 4;
+        const int C = target->dim / 32;
+        const long long rows_per_cta = (256 / (8 * C)) * U;
+        const unsigned grid = (unsigned)((n + rows_per_cta - 1) / rows_per_cta);
+        if (C == 1) k_target_manywell_v4<1, U><<<grid, 256, 0, st>>>(*target, (const float4*)d_x, d_log_p, (float4*)d_grad, (long long)n);
+        else if (C == 2) k_target_manywell_v4<2, U><<<grid, 256, 0, st>>>(*target, (const float4*)d_x, d_log_p, (float4*)d_grad, (long long)n);
+        else k_target_manywell_v4<4, U><<<grid, 256, 0, st>>>(*target, (const float4*)d_x, d_log_p, (float4*)d_grad, (long long)n);
+        CK_LAUNCH("k_target_manywell_v4");
+        return FAB_OK;
+    }
     const int nt = 256;
     const long long threads = n * 32;
     k_target<<<(unsigned)((threads + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
@@ -324,6 +341,13 @@ int fab_logw_update_f32(fab_gamma g, fab_gamma g_next, const float* d_log_q, con
     if (!d_log_q || !d_log_p || !d_log_w || n < 0)
         return fail(FAB_E_INVALID, "fab_logw_update_f32: bad arguments");
     if (n == 0) return FAB_OK;
+    if (aligned16(d_log_q) && aligned16(d_log_p) && aligned16(d_log_w) && n >= 4) {
+        const long long threads = (n >> 2) + (n & 3);
+        k_logw_update_v4<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            g, g_next, d_log_q, d_log_p, d_log_w, (long long)n);
+        CK_LAUNCH("k_logw_update_v4");
+        return FAB_OK;
+    }
     k_logw_update<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         g, g_next, d_log_q, d_log_p, d_log_w, (long long)n);
     CK_LAUNCH("k_logw_update");
@@ -398,6 +422,14 @@ int fab_gather_rows_f32(const float* d_src, float* d_dst, const int64_t* d_anc, 
     if (!d_src || !d_dst || !d_anc || n < 0 || row_floats < 1)
         return fail(FAB_E_INVALID, "fab_gather_rows_f32: bad arguments");
     if (n == 0) return FAB_OK;
+    if (row_floats % 4 == 0 && aligned16(d_src) && aligned16(d_dst)) {
+        constexpr int U = 4;
+        const long long tot4 = n * (row_floats / 4);
+        k_gather_rows_v4<U><<<(unsigned)((tot4 + 256 * U - 1) / (256 * U)), 256, 0, (cudaStream_t)stream>>>(
+            (const float4*)d_src, (float4*)d_dst, (const long long*)d_anc, (long long)n, row_floats / 4);
+        CK_LAUNCH("k_gather_rows_v4");
+        return FAB_OK;
+    }
     const long long tot = n * row_floats;
     k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_src, d_dst, (const long long*)d_anc, (long long)n, row_floats);
@@ -412,6 +444,15 @@ int fab_buffer_add_f32(float* d_buf_x, float* d_buf_log_w, float* d_buf_log_q, i
         current_index >= max_length || batch < 0 || batch > max_length || (batch > 0 && (!d_x || !d_log_w || !d_log_q)))
         return fail(FAB_E_INVALID, "fab_buffer_add_f32: bad arguments (batch <= max_length)");
     if (batch == 0) return FAB_OK;
+    if (dim % 4 == 0 && aligned16(d_buf_x) && aligned16(d_x)) {
+        constexpr int U = 4;
+        const long long tot4 = batch * (dim / 4);
+        k_buffer_add_v4<U><<<(unsigned)((tot4 + 256 * U - 1) / (256 * U)), 256, 0, (cudaStream_t)stream>>>(
+            (float4*)d_buf_x, d_buf_log_w, d_buf_log_q, (long long)max_length, dim / 4,
+            (long long)current_index, (const float4*)d_x, d_log_w, d_log_q, (long long)batch);
+        CK_LAUNCH("k_buffer_add_v4");
+        return FAB_OK;
+    }
     const long long tot = batch * dim;
     unsigned grid = (unsigned)((tot + 255) / 256);
     if (grid > 148u * 16u) grid = 148u * 16u;
@@ -423,9 +464,10 @@ int fab_buffer_add_f32(float* d_buf_x, float* d_buf_log_w, float* d_buf_log_q, i
     return FAB_OK;
 }
 
+// workspace: fab_sel_ctl | uint32 keys[n]
 int64_t fab_buffer_topk_workspace_bytes(int64_t n) {
     if (n < 0) return FAB_E_INVALID;
-    return n * 4 + 64;
+    return (int64_t)((sizeof(fab_sel_ctl) + 255) & ~(size_t)255) + n * 4 + 64;
 }
 
 int fab_buffer_topk_f32(const float* d_logits, const float* d_gumbel, int64_t n, int64_t k,
@@ -433,13 +475,28 @@ int fab_buffer_topk_f32(const float* d_logits, const float* d_gumbel, int64_t n,
     if (!d_logits || !d_gumbel || !d_indices || !d_workspace || n < 1 || k < 1 || k > n)
         return fail(FAB_E_INVALID, "fab_buffer_topk_f32: need 1 <= k <= n");
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned int* keys = (unsigned int*)d_workspace;
-    unsigned grid = (unsigned)((n + 255) / 256);
-    if (grid > 148u * 16u) grid = 148u * 16u;
-    k_buffer_keys<<<grid, 256, 0, s>>>(d_logits, d_gumbel, (long long)n, keys);
+    fab_sel_ctl* ctl = (fab_sel_ctl*)d_workspace;
+    unsigned int* keys = (unsigned int*)((char*)d_workspace + ((sizeof(fab_sel_ctl) + 255) & ~(size_t)255));
+    // CTA b owns a contiguous run of `chunk` keys (a multiple of the CTA width, >= 4096 keys)
+    long long nb = (n + 4095) / 4096;
+    if (nb > FAB_SEL_MAXB) nb = FAB_SEL_MAXB;
+    long long chunk = (n + nb - 1) / nb;
+    chunk = (chunk + FAB_SEL_NT - 1) / FAB_SEL_NT * FAB_SEL_NT;
+    const unsigned grid = (unsigned)((n + chunk - 1) / chunk);
+    cudaError_t e = cudaMemsetAsync(ctl, 0, offsetof(fab_sel_ctl, cnt), s);
+    if (e != cudaSuccess) return cuda_fail(e, "fab_buffer_topk_f32: memset");
+    k_buffer_keys<<<grid, FAB_SEL_NT, 0, s>>>(d_logits, d_gumbel, (long long)n, chunk, (long long)k,
+                                              keys, ctl);
     CK_LAUNCH("k_buffer_keys");
-    k_buffer_select<<<1, FAB_SEL_NT, 0, s>>>(keys, (long long)n, (long long)k, (long long*)d_indices);
-    CK_LAUNCH("k_buffer_select");
+    for (int pass = 1; pass < 4; ++pass) {
+        k_buffer_select_hist<<<grid, FAB_SEL_NT, 0, s>>>(keys, (long long)n, chunk, pass, ctl);
+        CK_LAUNCH("k_buffer_select_hist");
+    }
+    k_buffer_select_count<<<grid, FAB_SEL_NT, 0, s>>>(keys, (long long)n, chunk, ctl);
+    CK_LAUNCH("k_buffer_select_count");
+    k_buffer_select_scatter<<<grid, FAB_SEL_NT, 0, s>>>(keys, (long long)n, chunk, ctl,
+                                                        (long long*)d_indices);
+    CK_LAUNCH("k_buffer_select_scatter");
     return FAB_OK;
 }
 

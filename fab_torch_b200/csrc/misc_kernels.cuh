@@ -17,6 +17,54 @@ __global__ void k_target(fab_target_desc t, const float* __restrict__ x, float* 
     if (lane == 0) lp[row] = v;
 }
 
+// Streaming form of the many-well target for d = 32*C (C = 1, 2, 4): 8*C threads per row, one
+// float4 each, U rows per thread in flight (64 B/thread: enough outstanding bytes to fill HBM;
+// the warp-per-row form above keeps 4 B/thread in flight and stops at ~1.4 TB/s).  The per-row
+// sum is taken in EXACTLY the order of manywell_row + warp_sum -- "lane" l = (4*tr + c) % 32 first
+// accumulates its C chunks in sequence, then the xor-16/8/4/2/1 butterfly -- so both kernels return
+// the same bits (tests/test_gpu_misc.py::test_streaming_kernels_match_scalar_forms).
+template <int C, int U>
+__global__ void __launch_bounds__(256)
+k_target_manywell_v4(fab_target_desc t, const float4* __restrict__ x, float* __restrict__ lp,
+                     float4* __restrict__ g, long long n) {
+    constexpr int TPR = 8 * C;          // threads (float4s) per row
+    constexpr int RPW = 32 / TPR;       // rows per warp and load instruction
+    const int lane = threadIdx.x & 31;
+    const int tr = lane % TPR, grp = lane - tr;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long row0 = warp_id * (RPW * U) + lane / TPR;
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long row = row0 + u * RPW;
+        v[u] = row < n ? __ldcs(x + row * TPR + tr) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long row = row0 + u * RPW;
+        const float xv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float e[4], gj[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) manywell_elem(t, xv[c], c, e[c], gj[c]);   // parity of 4*tr+c = parity of c
+        if (g && row < n) __stcs(g + row * TPR + tr, make_float4(gj[0], gj[1], gj[2], gj[3]));
+        float a[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            a[c] = 0.f;
+#pragma unroll
+            for (int k = 0; k < C; ++k)         // chunk k of lane l lives in thread (tr % 8) + 8k
+                a[c] += __shfl_sync(FAB_FULL, e[c], grp + (tr & 7) + 8 * k);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)         // lane xor 16, 8, 4  ==  thread xor 4, 2, 1
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[c] += __shfl_xor_sync(FAB_FULL, a[c], o);
+        const float b0 = a[0] + a[2], b1 = a[1] + a[3];     // lane xor 2
+        const float s = b0 + b1;                            // lane xor 1
+        if (tr == 0 && row < n) lp[row] = -s - t.log_norm;
+    }
+}
+
 // ------------------------------------------------------------------ K11 log-weight update
 __global__ void k_logw_update(fab_gamma g, fab_gamma gn, const float* __restrict__ lq,
                               const float* __restrict__ lp, float* __restrict__ lw, long long n) {
@@ -24,6 +72,29 @@ __global__ void k_logw_update(fab_gamma g, fab_gamma gn, const float* __restrict
     if (i >= n) return;
     const float inc = __fsub_rn(gamma_of(gn, lq[i], lp[i]), gamma_of(g, lq[i], lp[i]));
     lw[i] = __fadd_rn(lw[i], inc);
+}
+// 16-byte form (all three pointers 16-byte aligned): thread i updates elements 4i..4i+3; the
+// n % 4 tail goes to the threads behind the last full float4.
+__global__ void __launch_bounds__(256)
+k_logw_update_v4(fab_gamma g, fab_gamma gn, const float* __restrict__ lq,
+                 const float* __restrict__ lp, float* __restrict__ lw, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n4 = n >> 2;
+    if (i < n4) {
+        const float4 q = __ldcs((const float4*)lq + i), p = __ldcs((const float4*)lp + i);
+        float4 w = __ldcs((const float4*)lw + i);
+        w.x = __fadd_rn(w.x, __fsub_rn(gamma_of(gn, q.x, p.x), gamma_of(g, q.x, p.x)));
+        w.y = __fadd_rn(w.y, __fsub_rn(gamma_of(gn, q.y, p.y), gamma_of(g, q.y, p.y)));
+        w.z = __fadd_rn(w.z, __fsub_rn(gamma_of(gn, q.z, p.z), gamma_of(g, q.z, p.z)));
+        w.w = __fadd_rn(w.w, __fsub_rn(gamma_of(gn, q.w, p.w), gamma_of(g, q.w, p.w)));
+        __stcs((float4*)lw + i, w);
+    } else {
+        const long long j = 4 * n4 + (i - n4);
+        if (j < n) {
+            const float inc = __fsub_rn(gamma_of(gn, lq[j], lp[j]), gamma_of(g, lq[j], lp[j]));
+            lw[j] = __fadd_rn(lw[j], inc);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ K12 NaN/inf filter
@@ -273,4 +344,30 @@ __global__ void k_gather_rows(const float* __restrict__ src, float* __restrict__
     const long long k = i / rowf;
     const int j = (int)(i - k * rowf);
     dst[i] = src[anc[k] * rowf + j];
+}
+// 16-byte form (row_floats % 4 == 0, both bases 16-byte aligned): a CTA copies a contiguous run
+// of 256*U float4s of `dst`; one 64-bit division per thread finds the run's first row, the rest
+// is 32-bit arithmetic.  All U loads are issued before the first store.
+template <int U>
+__global__ void __launch_bounds__(256)
+k_gather_rows_v4(const float4* __restrict__ src, float4* __restrict__ dst,
+                 const long long* __restrict__ anc, long long n, int rv) {
+    const long long tot = n * rv;
+    const long long base = (long long)blockIdx.x * (256 * U);
+    const long long k0 = base / rv;
+    const unsigned off0 = (unsigned)(base - k0 * rv) + threadIdx.x;
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned off = off0 + u * 256;
+        if (base + threadIdx.x + u * 256 < tot) {
+            const unsigned kr = off / (unsigned)rv, q = off - kr * (unsigned)rv;
+            v[u] = __ldg(src + __ldg(anc + k0 + kr) * rv + q);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long i = base + threadIdx.x + u * 256;
+        if (i < tot) __stcs(dst + i, v[u]);
+    }
 }

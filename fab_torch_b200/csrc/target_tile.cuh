@@ -6,20 +6,26 @@
 #pragma once
 #include "common.cuh"
 
+// One coordinate of the many-well energy and of d log p / d x.  Shared by the warp-per-row form
+// below and the streaming kernel in misc_kernels.cuh so both contract to the same FMAs.
+__device__ __forceinline__ void manywell_elem(const fab_target_desc& t, float v, int j, float& ej,
+                                              float& gj) {
+    if ((j & 1) == 0) {     // first coordinate of the pair: a x + b x^2 + c x^4
+        const float v2 = v * v;
+        ej = t.a * v + t.b * v2 + t.c * (v2 * v2);
+        gj = -(t.a + 2.f * t.b * v + 4.f * t.c * (v2 * v));
+    } else {                // second coordinate: x^2 / 2
+        ej = 0.5f * v * v;
+        gj = -v;
+    }
+}
+
 __device__ __forceinline__ float manywell_row(const fab_target_desc& t, const float* x, float* g,
                                               int d, int lane) {
     float e = 0.f;
     for (int j = lane; j < d; j += 32) {
-        const float v = x[j];
         float ej, gj;
-        if ((j & 1) == 0) {     // first coordinate of the pair: a x + b x^2 + c x^4
-            const float v2 = v * v;
-            ej = t.a * v + t.b * v2 + t.c * (v2 * v2);
-            gj = -(t.a + 2.f * t.b * v + 4.f * t.c * (v2 * v));
-        } else {                // second coordinate: x^2 / 2
-            ej = 0.5f * v * v;
-            gj = -v;
-        }
+        manywell_elem(t, x[j], j, ej, gj);
         e += ej;
         if (g) g[j] = gj;
     }

@@ -149,3 +149,68 @@ def test_global_resample_and_ess_trigger_single_process():
     res = fb.resample_if_ess_below(pt, lw, ess, threshold=min(1.0, ess * 2), u0=u0)
     assert res[2] is True and torch.equal(res[0].x, new.x)
     assert float(fb.effective_sample_size(res[1])) > 0.999         # uniform weights afterwards
+
+
+def _misaligned(t):
+    """Same values at an address 4 bytes past a 16-byte boundary -> the scalar kernel forms."""
+    buf = torch.empty(t.numel() + 4, dtype=t.dtype, device=t.device)
+    v = buf[1:1 + t.numel()].view(t.shape)
+    v.copy_(t)
+    assert v.data_ptr() % 16 != 0
+    return v
+
+
+@pytest.mark.parametrize("dim", [32, 64, 128])
+@pytest.mark.parametrize("n", [1, 5, 1023, 40000])
+def test_streaming_target_matches_warp_per_row_form(dim, n):
+    """k_target_manywell_v4 (16-byte loads, several rows per thread) sums each row in the order of
+    manywell_row + warp_sum: identical bits to k_target, NaN/inf rows included."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(dim + n)
+    x = (torch.randn(n, dim, generator=g) * 1.9).cuda()
+    if n > 4:
+        x[2, 3] = float("nan")
+        x[3, 0] = float("inf")
+    tgt = fb.ManyWellEnergy(dim)
+    desc = tgt.target_desc(x.device)
+    out = []
+    for xin in (x, _misaligned(x)):
+        lp = torch.empty(n, device="cuda")
+        gr = torch.empty(n, dim, device="cuda")
+        _lib.check(L.fab_target_logprob_grad_f32(desc, _lib.ptr(xin), _lib.ptr(lp), _lib.ptr(gr), n,
+                                                 _lib.stream_ptr()))
+        lp2 = torch.empty(n, device="cuda")
+        _lib.check(L.fab_target_logprob_grad_f32(desc, _lib.ptr(xin), _lib.ptr(lp2), None, n,
+                                                 _lib.stream_ptr()))
+        assert torch.equal(lp.view(torch.int32), lp2.view(torch.int32))        # value-only form
+        out.append((lp, gr))
+    assert torch.equal(out[0][0].view(torch.int32), out[1][0].view(torch.int32))
+    assert torch.equal(out[0][1].view(torch.int32), out[1][1].view(torch.int32))
+
+
+@pytest.mark.parametrize("n", [3, 4, 4099, 100001])
+def test_logw_update_vector_form_matches_scalar(n):
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(n)
+    lq, lp, lw = (torch.randn(n, generator=g).cuda() * s for s in (50.0, 30.0, 10.0))
+    ga, gb = fb.make_gamma(0.25, 2.0, False), fb.make_gamma(0.3125, 2.0, False)
+    a, b = lw.clone(), _misaligned(lw)
+    _lib.check(L.fab_logw_update_f32(ga, gb, _lib.ptr(lq), _lib.ptr(lp), _lib.ptr(a), n, _lib.stream_ptr()))
+    _lib.check(L.fab_logw_update_f32(ga, gb, _lib.ptr(lq), _lib.ptr(lp), _lib.ptr(b), n, _lib.stream_ptr()))
+    assert torch.equal(a, b) and not torch.equal(a, lw)
+
+
+@pytest.mark.parametrize("rowf", [1, 4, 32, 60, 98, 128])
+@pytest.mark.parametrize("n", [1, 777, 20011])
+def test_gather_rows_all_forms(rowf, n):
+    """fab_gather_rows_f32: 16-byte form (row_floats % 4 == 0) and scalar form == torch indexing."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(rowf * 7 + n)
+    m = max(n // 2, 1)
+    src = torch.randn(m, rowf, generator=g).cuda()
+    anc = torch.randint(0, m, (n,), generator=g).cuda()
+    for s in (src, _misaligned(src)):
+        dst = torch.empty(n, rowf, device="cuda")
+        _lib.check(L.fab_gather_rows_f32(_lib.ptr(s), _lib.ptr(dst), _lib.ptr(anc), n, rowf,
+                                         _lib.stream_ptr()))
+        assert torch.equal(dst, src[anc])
