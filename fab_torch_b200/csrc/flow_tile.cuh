@@ -21,6 +21,16 @@
 #pragma once
 #include "mma_gemm.cuh"
 
+// FAB_PF_EARLY (experiment knob): issue the L1 prefetch of a GEMM's first weight words before the
+// PREVIOUS GEMM starts instead of behind it.
+#ifdef FAB_PF_EARLY
+#define PF_E(x) x
+#define PF_L(x)
+#else
+#define PF_E(x)
+#define PF_L(x) x
+#endif
+
 struct TileBufs {
     float *gs, *par, *h1, *h2, *red, *sy2, *ses, *ld, *scl;
     float *loc, *lsc, *inv, *logs;          // staged constants
@@ -124,21 +134,23 @@ __device__ __forceinline__ void hidden_bwd(float* dst, const uint32_t* mask, int
 // `next_wf` describes the GEMM that follows the coupling step (prefetched behind the last barrier).
 template <int TP, bool SAVE>
 __device__ __forceinline__ int mlp_tail(const TileLayout& L, const float* __restrict__ lay, const fab_flow_desc& f,
-                                        int k, const float* next_wf, int next_NT, bool next_ksplit) {
+                                        int k, const float* next_wf, int next_NT, bool next_ksplit, int next_KT2) {
     const TileBufs b = tile_bufs(L);
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     uint32_t* m2 = SAVE ? b.m2 + (size_t)k * L.MW : nullptr;
     float* h2 = b.h2;
+    PF_E(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w3), L.P8 / 8, true, L.W16 / 16);)
     mma_gemm_wide<TP>(b.h1, L.W16 / 16, reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH,
                       lay + f.o_b2, [&](int nt, const float (&c)[4]) {
                           hidden_fwd<TP, SAVE>(h2, m2, nt, g, t, c);
                       });
-    mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w3), L.P8 / 8, true);
+    PF_L(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w3), L.P8 / 8, true, L.W16 / 16);)
     __syncthreads();
     prof_mark(5);
+    PF_E(if (next_wf) mma_prefetch(reinterpret_cast<const float4*>(next_wf), next_NT, next_ksplit, next_KT2);)
     const int KSe = mma_gemm_ksplit<TP>(b.h2, L.W16 / 16, reinterpret_cast<const float4*>(lay + f.o_w3),
                                         L.P8 / 8, b.red);
-    if (next_wf) mma_prefetch(reinterpret_cast<const float4*>(next_wf), next_NT, next_ksplit);
+    PF_L(if (next_wf) mma_prefetch(reinterpret_cast<const float4*>(next_wf), next_NT, next_ksplit, next_KT2);)
     __syncthreads();
     prof_mark(7);
     return KSe;
@@ -190,6 +202,7 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
             if (nt < NTV) frag_store<TP>(zn, 8 * nt, g, t, c[0], c[1], c[2], c[3]);
             else hidden_fwd<TP, SAVE>(h1, m1, nt - NTV, g, t, c);
         };
+        PF_E(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false, L.W16 / 16);)
         // 41..48 tiles (config 2: 4 + 40): six per warp in ONE pass instead of a nearly empty second
         if (NT1 > 8 * FAB_NTW && NT1 <= 8 * (FAB_NTW + 1))
             mma_gemm_wide_n<TP, FAB_NTW + 1>(zsel(L, cur), L.D16 / 16,
@@ -197,11 +210,11 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
         else
             mma_gemm_wide<TP>(zsel(L, cur), L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mw1), NT1,
                               lay + f.o_b1, epi1);
-        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false);
+        PF_L(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false, L.W16 / 16);)
         __syncthreads();
         prof_mark(3);
         const int KSe = mlp_tail<TP, SAVE>(L, lay, f, k,
-                                           k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr, NT1, false);
+                                           k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr, NT1, false, L.D16 / 16);
         // coupling inverse: y2 = (v2 - shift) * exp(-scale)
         {
             const float* b3 = lay + f.o_b3;
@@ -279,31 +292,35 @@ __device__ void flow_backward(const TileLayout& L, const fab_flow_desc& f,
         {
             float* h2 = b.h2;
             const uint32_t* m2 = b.m2 + (size_t)k * L.MW;
+            PF_E(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2t), L.NTH, false, L.W16 / 16);)
             mma_gemm_wide<TP>(b.par, L.P16 / 16, reinterpret_cast<const float4*>(lay + f.o_w3t), L.NTH,
                               nullptr, [&](int nt, const float (&c)[4]) {
                                   hidden_bwd<TP>(h2, m2, nt, g, t, c);
                               });
         }
-        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2t), L.NTH, false);
+        PF_L(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2t), L.NTH, false, L.W16 / 16);)
         __syncthreads();
         prof_mark(11);
         // gh1 = (gh2 @ W2) * m1
         {
             float* h1 = b.h1;
             const uint32_t* m1 = b.m1 + (size_t)k * L.MW;
+            PF_E(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, true, (L.W16 + L.D16) / 16);)
             mma_gemm_wide<TP>(b.h2, L.W16 / 16, reinterpret_cast<const float4*>(lay + f.o_w2t), L.NTH,
                               nullptr, [&](int nt, const float (&c)[4]) {
                                   hidden_bwd<TP>(h1, m1, nt, g, t, c);
                               });
         }
-        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, true);
+        PF_L(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, true, (L.W16 + L.D16) / 16);)
         __syncthreads();
         prof_mark(13);
+        PF_E(if (k + 1 < L.K)
+            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t), L.NTH, false, L.P16 / 16);)
         // g_u = [gh1 | gv] @ [W1 Wmix[:, :d1]^T ; Wmix^T]
         const int KSe = mma_gemm_ksplit<TP>(b.h1, (L.W16 + L.D16) / 16,
                                             reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, b.red);
-        if (k + 1 < L.K)
-            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t), L.NTH, false);
+        PF_L(if (k + 1 < L.K)
+            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t), L.NTH, false, L.P16 / 16);)
         __syncthreads();
         prof_mark(15);
         for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
@@ -346,9 +363,9 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
                                   hidden_fwd<TP, false>(h1, nullptr, nt, g, t, c);
                               });
         }
-        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false);
+        mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w2), L.NTH, false, L.W16 / 16);
         __syncthreads();
-        const int KSe = mlp_tail<TP, false>(L, lay, f, k, lay + f.o_mix_inv, L.D8 / 8, true);
+        const int KSe = mlp_tail<TP, false>(L, lay, f, k, lay + f.o_mix_inv, L.D8 / 8, true, L.D16 / 16);
         {
             const float* b3 = lay + f.o_b3;
             for (int e = threadIdx.x; e < L.d2 * TP; e += FAB_NT) {
@@ -365,7 +382,7 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
         const int KS2 = mma_gemm_ksplit<TP>(z, L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mix_inv),
                                             L.D8 / 8, b.red);
         if (k + 1 < L.K)
-            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w1), L.NTH, false);
+            mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w1), L.NTH, false, L.D1K / 16);
         __syncthreads();
         for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
             const int j = e / TP, p = e - j * TP;

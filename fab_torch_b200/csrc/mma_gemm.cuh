@@ -44,12 +44,31 @@ template <int TP> struct ActL {
     static constexpr int RS = TP == 16 ? 20 : 12;     // partial-sum slot stride (conflict-free stores)
 };
 
+// Weight words are read once per CTA (no L1 allocation) but by every CTA and every launch: they
+// must stay in L2.  Plain loads insert at normal priority, and once L2 is full of other data at
+// the same priority (e.g. after a 256 MB fill between calls) the streamed blob keeps missing:
+// measured +15 % cycles per k_hmc_step launch, persisting long after the fill
+// (profiles/ab_clock.py).  The evict_last policy keeps the blob resident.
+#ifndef FAB_NO_L2_HINT
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(l2_keep_policy()));
+    return r;
+}
+#else
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
     asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+#endif
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(v) & 0xffffe000u;
@@ -130,21 +149,31 @@ __device__ __forceinline__ void mma_pair(float (&c)[NT_][4], const float* act, i
     }
 }
 
-// Pull the first weight words a following GEMM will read into L1 while an epilogue runs.
-__device__ __forceinline__ void mma_prefetch(const float4* __restrict__ Wf, int NT, bool ksplit) {
+// Pull the first weight words a following GEMM will read into L1 while an epilogue runs: the
+// first FAB_PF_DEPTH k-tile pairs (= the three ring stages the GEMM prologue loads) of the warp's
+// own tiles.  KT2 = k-tile pairs of that GEMM.
+#ifndef FAB_PF_DEPTH
+#define FAB_PF_DEPTH 1
+#endif
+__device__ __forceinline__ void mma_prefetch(const float4* __restrict__ Wf, int NT, bool ksplit, int KT2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int nt0, kp0, stride, cnt;
+    int nt0, kp0, stride, cnt, kstep;
     if (ksplit) {
         int NGR, KS; fab_ksplit_plan(NT, NGR, KS);
-        nt0 = warp % NGR; kp0 = warp / NGR; stride = NGR; cnt = FAB_NTK;
+        nt0 = warp % NGR; kp0 = warp / NGR; stride = NGR; cnt = FAB_NTK; kstep = KS < KT2 ? KS : KT2;
     } else {
-        nt0 = warp; kp0 = 0; stride = 8; cnt = FAB_NTW;
+        nt0 = warp; kp0 = 0; stride = 8; cnt = FAB_NTW; kstep = 1;
     }
     // (a k-split warp whose first k-pair does not exist prefetches a word of the next operand:
     // harmless, the blob is contiguous and padded)
-    const float4* p = Wf + ((size_t)kp0 * NT + nt0) * 32 + lane;
-    for (int i = 0; i < cnt; ++i)
-        if (nt0 + stride * i < NT) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (size_t)i * stride * 32));
+#pragma unroll
+    for (int dd = 0; dd < FAB_PF_DEPTH; ++dd) {
+        const int kp = kp0 + dd * kstep;
+        if (dd > 0 && kp >= KT2) break;
+        const float4* p = Wf + ((size_t)kp * NT + nt0) * 32 + lane;
+        for (int i = 0; i < cnt; ++i)
+            if (nt0 + stride * i < NT) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (size_t)i * stride * 32));
+    }
 }
 
 // Wide GEMM.  Warp w owns the n-tiles nt = base + w + 8*i (i < FAB_NTW) of every pass
