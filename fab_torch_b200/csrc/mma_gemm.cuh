@@ -149,11 +149,17 @@ __device__ __forceinline__ void mma_pair(float (&c)[NT_][4], const float* act, i
     }
 }
 
-// Pull the first weight words a following GEMM will read into L1 while an epilogue runs: the
-// first FAB_PF_DEPTH k-tile pairs (= the three ring stages the GEMM prologue loads) of the warp's
-// own tiles.  KT2 = k-tile pairs of that GEMM.
+// Optional L1 prefetch of the first weight words a following GEMM will read (the first
+// FAB_PF_DEPTH k-tile pairs of the warp's own tiles; KT2 = k-tile pairs of that GEMM).
+// OFF by default: measured on B200 with the L2 evict_last policy in place, chain time at depth
+// 0 / 1 / 2 / 3 = 24.24 / 24.77 / 25.74 / 25.81 ms (profiles/ab_chain.py) -- the no-allocate
+// loads do not hit the prefetched lines, so a prefetch is a second L2 read of the same line.
+// Two deeper variants were measured as well and are slower still: issuing the prefetch one GEMM
+// earlier (-DFAB_PF_EARLY, 24.72 at depth 1) and carrying the register ring ACROSS GEMMs so that
+// the next GEMM's first three stages load during the epilogue and barrier (28.3 ms: the ring
+// registers stay live through every epilogue; profiles/experiments/cross_gemm_ring.patch).
 #ifndef FAB_PF_DEPTH
-#define FAB_PF_DEPTH 1
+#define FAB_PF_DEPTH 0
 #endif
 __device__ __forceinline__ void mma_prefetch(const float4* __restrict__ Wf, int NT, bool ksplit, int KT2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
