@@ -1,6 +1,6 @@
 """Target densities of the hot path with closed-form gradients evaluated on the device.
 
-  ManyWellEnergy  fab/target_distributions/many_well.py:16-90 (+ double_well.py:44-58,97-103)
+  ManyWellEnergy  fab/target_distributions/many_well.py:16-147 (+ double_well.py:44-103)
   GMM             fab/target_distributions/gmm.py:12-66
   DiagGaussianTarget  stand-in for the `WrappedTorchDist(MultivariateNormal(loc, s*I))` targets of
                   the reference's own tests (fab/sampling_methods/ais_test.py:32-33)
@@ -49,8 +49,39 @@ class _DeviceTarget(nn.Module, TargetDistribution):
         raise NotImplementedError
 
 
+class _ChunkedDataset:
+    """Batches of a test set (fab/utils/training.py:36-53).  Like the reference it yields chunks of
+    size ceil(N / batch_size) -- `torch.split` is given the number of splits as the chunk size."""
+
+    def __init__(self, batch_size: int, dataset: torch.Tensor, device):
+        self.batch_size = batch_size
+        self.n_splits = int(np.ceil(dataset.shape[0] / batch_size))
+        self._chunks = iter(torch.split(dataset, self.n_splits))
+        self.device = device
+        self.test_set_n_points = dataset.shape[0]
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return next(self._chunks).to(self.device)
+
+    def __len__(self):
+        return self.n_splits
+
+
 class ManyWellEnergy(_DeviceTarget):
-    """d/2 copies of the 2-D double well E = a x1 + b x1^2 + c x1^4 + x2^2/2."""
+    """d/2 copies of the 2-D double well E = a x1 + b x1^2 + c x1^4 + x2^2/2.
+
+    Hot path: `log_prob` / `target_desc` (CUDA kernels).  Evaluation path (host
+    logic in torch on `self.device`, same RNG calls in the same order as the reference):
+    `sample` (many_well.py:61-67, double_well.py:60-94, rejection_sampling.py:6-20),
+    `get_modes_test_set_iterator` (many_well.py:69-79) and `performance_metrics`
+    (many_well.py:96-147), which is what `FABModel.get_eval_info` (fab/core.py:191-220) calls."""
+
+    centre = 1.7
+    max_dim_for_all_modes = 40          # a full mode test set has 2^(d/2) rows
+    _Z_FIRST_DIM = 11784.50927          # double_well.py:68
 
     def __init__(self, dim: int = 4, use_gpu: bool = True, normalised: bool = False,
                  a: float = -0.5, b: float = -6.0, c: float = 1.0):
@@ -60,12 +91,32 @@ class ManyWellEnergy(_DeviceTarget):
         self.n_wells = dim // 2
         self._a, self._b, self._c = a, b, c
         self.normalised = normalised
+        if self._default_well:          # proposal of the exact sampler (double_well.py:38-41)
+            self.register_buffer("component_mix", torch.tensor([0.2, 0.8]))
+            self.register_buffer("means", torch.tensor([-1.7, 1.7]))
+            self.register_buffer("scales", torch.tensor([0.5, 0.5]))
+        if dim < self.max_dim_for_all_modes:
+            # every sign pattern of +-centre on the first coordinate of each well, first well
+            # slowest (the reference's meshgrid order, many_well.py:27-35)
+            n = self.n_wells
+            bits = (torch.arange(2 ** n)[:, None] >> torch.arange(n - 1, -1, -1)[None, :]) & 1
+            modes = torch.zeros((2 ** n, dim))
+            modes[:, 0::2] = (2.0 * bits - 1.0) * self.centre
+            self.register_buffer("_test_set_modes", modes)
+        self.shallow_well_bounds = [-1.75, -1.65]
+        self.deep_well_bounds = [1.7, 1.8]
         self.device = "cuda" if (use_gpu and torch.cuda.is_available()) else "cpu"
+        if self.device == "cuda":
+            self.cuda()
+
+    @property
+    def _default_well(self) -> bool:
+        return self._a == -0.5 and self._b == -6 and self._c == 1.0
 
     @property
     def log_Z_2D(self):
-        if self._a == -0.5 and self._b == -6 and self._c == 1.0:
-            return np.log(11784.50927) + 0.5 * np.log(2 * torch.pi)   # double_well.py:97-103
+        if self._default_well:
+            return np.log(self._Z_FIRST_DIM) + 0.5 * np.log(2 * torch.pi)   # double_well.py:97-103
         raise NotImplementedError
 
     @property
@@ -79,6 +130,83 @@ class ManyWellEnergy(_DeviceTarget):
     def target_desc(self, device=None):
         return _lib.TargetDesc(_lib.FAB_TARGET_MANYWELL, self.dim, 0, 0, self._a, self._b, self._c,
                                float(self.log_Z) if self.normalised else 0.0, None, None, None)
+
+    # ------------------------------------------------------------------ evaluation path
+    def _sample_first_dimension(self, n: int) -> torch.Tensor:
+        """Rejection sampling of exp(-x^4 + 6x^2 + x/2) under 3 Z * (0.2 N(-1.7,.5) + 0.8 N(1.7,.5)):
+        draw 10x the missing count, keep the accepted ones in order, repeat for the remainder."""
+        if not self._default_well:
+            raise NotImplementedError
+        k = self._Z_FIRST_DIM * 3
+        prop = torch.distributions.MixtureSameFamily(
+            mixture_distribution=torch.distributions.Categorical(self.component_mix),
+            component_distribution=torch.distributions.Normal(self.means, self.scales))
+        kept, missing = [], n
+        while missing > 0:
+            z = prop.sample((missing * 10,))
+            u = torch.distributions.Uniform(0, k * torch.exp(prop.log_prob(z))).sample().to(z)
+            log_t = -(z ** 4)
+            log_t = log_t + 6 * z ** 2
+            log_t = log_t + 1 / 2 * z
+            ok = z[torch.exp(log_t) > u][:missing]
+            kept.append(ok)
+            missing -= ok.shape[0]
+        return kept[0] if len(kept) == 1 else torch.concat(kept, dim=0)
+
+    def sample(self, shape):
+        """Exact samples: per well, x1 by rejection sampling, x2 ~ N(0, 1)."""
+        assert len(shape) == 1
+        wells = []
+        for _ in range(self.n_wells):
+            x1 = self._sample_first_dimension(shape[0])
+            x2 = torch.distributions.Normal(torch.tensor(0.0).to(x1.device),
+                                            torch.tensor(1.0).to(x1.device)).sample(shape)
+            wells.append(torch.stack([x1, x2], dim=-1))
+        return torch.concat(wells, dim=-1)
+
+    def get_modes_test_set_iterator(self, batch_size: int):
+        """Points placed at the modes: all of them below 40 dimensions, 10^4 random ones above."""
+        if self.dim < self.max_dim_for_all_modes:
+            test_set = self._test_set_modes
+        else:
+            outer = int(1e4)
+            test_set = torch.zeros((outer, self.dim))
+            test_set[:, torch.arange(self.dim) % 2 == 0] = \
+                -self.centre + self.centre * 2 * torch.randint(high=2, size=(outer, int(self.dim / 2)))
+        return _ChunkedDataset(batch_size=batch_size, dataset=test_set, device=self.device)
+
+    def performance_metrics(self, samples: torch.Tensor, log_w: torch.Tensor,
+                            log_q_fn=None, batch_size: Optional[int] = None):
+        """log-Z accuracy of 50 interleaved sub-estimates and, given the model density, its mean
+        log-likelihood on the mode test set and on exact samples + the forward KL.  Quirks of the
+        reference kept: `split(50)` chunks have SIZE 50; the number of exact-sample batches is
+        read off the stacked tensor's first axis, i.e. max(50 // batch_size, 1)."""
+        del samples
+        n_runs = 50
+        keep = (log_w.shape[0] // n_runs) * n_runs
+        stacked = torch.stack(log_w[:keep].split(n_runs), dim=-1)
+        log_Z_estimate = torch.logsumexp(stacked, dim=-1) - np.log(stacked.shape[-1])
+        relative_error = torch.exp(log_Z_estimate - self.log_Z) - 1
+        info = dict(relative_MSE_Z_estimate=torch.mean(torch.abs(relative_error)).cpu().item(),
+                    abs_MSE_log_Z_estimate=torch.mean(torch.abs(log_Z_estimate - self.log_Z)).cpu().item())
+        if log_q_fn is None:
+            return info
+        assert batch_size is not None
+        n_batches = max(stacked.shape[0] // batch_size, 1)
+        sum_modes, sum_exact, sum_kl = 0.0, 0.0, 0.0
+        modes = self.get_modes_test_set_iterator(batch_size=batch_size)
+        for x in modes:
+            sum_modes += torch.sum(log_q_fn(x)).detach().cpu()
+        for _ in range(n_batches):
+            x = self.sample((batch_size,))
+            log_q = log_q_fn(x)
+            sum_exact += torch.sum(log_q).detach().cpu()
+            sum_kl += torch.sum(self.log_prob(x) - self.log_Z - log_q).detach().cpu()
+        m = batch_size * n_batches
+        info.update(test_set_modes_mean_log_prob=(sum_modes / modes.test_set_n_points).cpu().item(),
+                    test_set_exact_mean_log_prob=(sum_exact / m).cpu().item(),
+                    forward_kl=(sum_kl / m).cpu().item(), eval_batch_size=m)
+        return info
 
 
 class GMM(_DeviceTarget):

@@ -1,0 +1,62 @@
+"""CPU: the Many-Well evaluation path -- oracle/eval_manywell.py and the
+product's host logic against the golden fixture written by the UNMODIFIED reference
+(oracle/gen_golden_eval.py): exact sampler, mode test set, test-set iterator, performance_metrics."""
+import math
+
+import pytest
+import torch
+
+import fab_torch_b200 as fb
+from golden_util import load_fixture
+from oracle import eval_manywell as ev
+from oracle.targets import OracleManyWell
+
+
+def std_normal_log_prob(x):
+    return -0.5 * (x ** 2).sum(-1) - 0.5 * x.shape[-1] * math.log(2 * math.pi)
+
+
+@pytest.mark.parametrize("dim", [4, 8])
+def test_oracle_reproduces_reference_eval(dim):
+    e = load_fixture("eval_manywell")[dim]
+    orc = OracleManyWell(dim)
+    torch.manual_seed(e["seed"])
+    assert torch.equal(ev.sample_many_well(dim, (257,)), e["samples"])
+    assert ev.performance_metrics(orc, e["log_w"]) == e["metrics_no_q"]
+    for bs, m in e["metrics_q"].items():
+        torch.manual_seed(m["seed"])
+        assert ev.performance_metrics(orc, e["log_w"], std_normal_log_prob, bs) == m["info"]
+    it, n = ev.modes_test_set(dim, 10)
+    assert [x.shape[0] for x in it] == e["iterator_chunk_sizes_bs10"] and n == 2 ** (dim // 2)
+
+
+@pytest.mark.parametrize("dim", [4, 8])
+def test_product_host_logic_reproduces_reference_eval(dim):
+    """Same torch RNG calls in the same order -> the product's sampler / metrics give the
+    reference's bits on the CPU (the log_q / log_p evaluations of the full metric need the GPU:
+    tests/test_gpu_eval.py)."""
+    e = load_fixture("eval_manywell")[dim]
+    tgt = fb.ManyWellEnergy(dim, use_gpu=False)
+    torch.manual_seed(e["seed"])
+    assert torch.equal(tgt.sample((257,)), e["samples"])
+    assert tgt.performance_metrics(None, e["log_w"]) == e["metrics_no_q"]
+    assert torch.equal(tgt._test_set_modes, ev.mode_test_set(dim))
+    it = tgt.get_modes_test_set_iterator(10)
+    assert [x.shape[0] for x in it] == e["iterator_chunk_sizes_bs10"]
+    assert it.test_set_n_points == 2 ** (dim // 2)
+    with pytest.raises(RuntimeError):                     # no CPU fallback for the density itself
+        tgt.performance_metrics(None, e["log_w"], std_normal_log_prob, 10)
+
+
+def test_mode_test_set_shapes_and_sampler_statistics():
+    assert fb.ManyWellEnergy(32, use_gpu=False)._test_set_modes.shape == (65536, 32)
+    assert not hasattr(fb.ManyWellEnergy(40, use_gpu=False), "_test_set_modes")
+    big = fb.ManyWellEnergy(40, use_gpu=False).get_modes_test_set_iterator(1000)
+    x = next(big)
+    assert x.shape[1] == 40 and bool((x[:, 1::2] == 0).all()) and bool(torch.allclose(x[:, 0].abs(), torch.full_like(x[:, 0], 1.7)))
+    torch.manual_seed(0)
+    xs = fb.ManyWellEnergy(2, use_gpu=False).sample((40000,))
+    right = (xs[:, 0] > 0).float().mean().item()
+    # mass of the deep well: int_{x>0} exp(-x^4+6x^2+x/2) / Z = 0.8443 (quadrature)
+    assert abs(right - 0.8443) < 0.01
+    assert abs(xs[:, 1].mean().item()) < 0.02 and abs(xs[:, 1].var().item() - 1.0) < 0.03
