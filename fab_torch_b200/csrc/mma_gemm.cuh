@@ -193,40 +193,11 @@ __device__ __forceinline__ void mma_gemm_wide_n(const float* act, int KT2, const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int npass = (NT + 8 * NTW - 1) / (8 * NTW);
     const int total = npass * KT2;
-    // prefetch cursor (pass, kp) of the weight ring
+    // prefetch cursor (pass, kp) of the weight ring.  (A leaner cursor -- running pointer, per-pass
+    // tile count, unpredicated loads for full passes -- executes fewer instructions but was
+    // measured slower, 25.46 vs 24.24 ms per chain: its extra branches cost more than the
+    // address arithmetic it saves.)
     int pf_base = 0, pf_kp = 0, pf_it = 0;
-#ifdef FAB_RING_LEAN
-    // Lean cursor (experiment knob, default off until measured on the GPU): a running pointer (one
-    // 64-bit add per stage) and a per-pass tile count instead of re-deriving the address and five
-    // tile predicates for every stage.  profiles/r01_hot_lines.md charges the bookkeeping of the
-    // default form (the lines of the lambda below) with 16 % of the kernel's instructions.
-    const float4* pf_p = Wf + (size_t)warp * 32 + lane;
-    const size_t pf_kstride = (size_t)NT * 32;
-    auto owned = [&](int base) {
-        int c = (NT - base - warp + 7) / 8;
-        return c > NTW ? NTW : (c < 0 ? 0 : c);
-    };
-    int pf_cnt = owned(0);
-    auto fetch = [&](float4 (&dst)[NTW]) {
-        if (pf_it < total) {
-            if (pf_cnt == NTW) {
-#pragma unroll
-                for (int i = 0; i < NTW; ++i) dst[i] = ldg_stream(pf_p + (size_t)i * 8 * 32);
-            } else {
-#pragma unroll
-                for (int i = 0; i < NTW; ++i)
-                    if (i < pf_cnt) dst[i] = ldg_stream(pf_p + (size_t)i * 8 * 32);
-            }
-            pf_p += pf_kstride;
-            ++pf_it;
-            if (++pf_kp == KT2) {               // next pass: k-pair 0 of the tiles 8*NTW further on
-                pf_kp = 0; pf_base += 8 * NTW;
-                pf_p = Wf + ((size_t)pf_base + warp) * 32 + lane;
-                pf_cnt = owned(pf_base);
-            }
-        }
-    };
-#else
     auto fetch = [&](float4 (&dst)[NTW]) {
         if (pf_it < total) {
             const float4* p = Wf + ((size_t)pf_kp * NT + pf_base + warp) * 32 + lane;
@@ -237,7 +208,6 @@ __device__ __forceinline__ void mma_gemm_wide_n(const float* act, int KT2, const
             if (++pf_kp == KT2) { pf_kp = 0; pf_base += 8 * NTW; }
         }
     };
-#endif
     // three-deep register ring: the main loop is unrolled by three so that no register moves are
     // needed; each buffer is refilled (for the pair three steps ahead) right after its use.
     // (profiles/microbench_mma_variants.cu times the alternatives in isolation -- two-deep ring,
