@@ -234,6 +234,31 @@ __device__ __forceinline__ void mma_gemm_wide_n(const float* act, int KT2, const
             c[i][0] = b0; c[i][1] = b1; c[i][2] = b0; c[i][3] = b1;
         }
         int kp = 0;
+#ifdef FAB_RING_PEEL
+        // Experiment knob (default off, NOT yet measured): branch-free steady state for single-pass
+        // GEMMs.  While three more stages exist the refills need no guard, no tile predicate and
+        // no address arithmetic beyond one running pointer; the guarded loops below drain the
+        // last 3..5 k-tile pairs.  (profiles/r01_hot_lines.md: the guarded cursor is 16 % of the
+        // kernel's instructions; a leaner but branchy cursor was slower.)
+        if (npass == 1 && cnt >= NTW - 1 && KT2 >= 6) {
+            const size_t kstr = (size_t)NT * 32;
+            const float4* q = Wf + (3 * kstr + (size_t)warp * 32 + lane);      // stage 3
+#define FAB_PEEL3(CNT)                                                                        \
+            for (; kp + 6 <= KT2; kp += 3) {                                                   \
+                mma_pair<TP, NTW, CNT>(c, act, kp * 16, g, t, w0, cnt);                        \
+                _Pragma("unroll") for (int i = 0; i < CNT; ++i) w0[i] = ldg_stream(q + (size_t)i * 8 * 32);            \
+                mma_pair<TP, NTW, CNT>(c, act, kp * 16 + 16, g, t, w1, cnt);                   \
+                _Pragma("unroll") for (int i = 0; i < CNT; ++i) w1[i] = ldg_stream(q + kstr + (size_t)i * 8 * 32);     \
+                mma_pair<TP, NTW, CNT>(c, act, kp * 16 + 32, g, t, w2, cnt);                   \
+                _Pragma("unroll") for (int i = 0; i < CNT; ++i) w2[i] = ldg_stream(q + 2 * kstr + (size_t)i * 8 * 32); \
+                q += 3 * kstr;                                                                 \
+            }
+            if (cnt == NTW) { FAB_PEEL3(NTW) }
+            else { FAB_PEEL3(NTW - 1) }
+#undef FAB_PEEL3
+            pf_kp = pf_it = kp + 3;             // stages fetched so far; the guarded cursor takes over
+        }
+#endif
 #define FAB_RING3(CNT)                                                        \
         for (; kp + 3 <= KT2; kp += 3) {                                       \
             mma_pair<TP, NTW, CNT>(c, act, kp * 16, g, t, w0, cnt);            \
