@@ -213,9 +213,22 @@ class GMM(_DeviceTarget):
     """Equal-weight mixture of `n_mixes` isotropic Gaussians.  Construction draws the means with
     `torch.rand((n_mixes, dim))` exactly like gmm.py:22, so the same seed gives the same target."""
 
-    def __init__(self, dim, n_mixes, loc_scaling, log_var_scaling=0.1, seed=0, use_gpu=True):
+    # evaluation path (class-level defaults so that subclasses with their own constructor have them)
+    n_test_set_samples = 1000
+    true_expectation_estimation_n_samples = int(1e7)
+    _true_expectation = None
+    _quad_tables = None
+
+    def __init__(self, dim, n_mixes, loc_scaling, log_var_scaling=0.1, seed=0,
+                 n_test_set_samples=1000, use_gpu=True,
+                 true_expectation_estimation_n_samples=int(1e7)):
+        """Same signature as gmm.py:13-15.  Unlike the reference, the Monte-Carlo estimate of the
+        test function's true expectation (10^7 samples by default, and a re-seeding of the global
+        RNG as a side effect) is NOT run here but on first use (`true_expectation`)."""
         super().__init__()
         self.seed, self.n_mixes, self.dim = seed, n_mixes, dim
+        self.n_test_set_samples = n_test_set_samples
+        self.true_expectation_estimation_n_samples = true_expectation_estimation_n_samples
         mean = (torch.rand((n_mixes, dim)) - 0.5) * 2 * loc_scaling
         log_var = torch.ones((n_mixes, dim)) * log_var_scaling
         self.register_buffer("cat_probs", torch.ones(n_mixes))
@@ -255,6 +268,56 @@ class GMM(_DeviceTarget):
 
     def sample(self, shape=(1,)):
         return self.distribution.sample(shape)
+
+    # ------------------------------------------------------------------ evaluation path
+    # gmm.py:53-55,71-99 + fab/utils/numerical.py:8-15,25-60 (host logic in torch; the densities
+    # themselves go through the CUDA kernels)
+    @property
+    def test_set(self) -> torch.Tensor:
+        """A FRESH sample set on every access, like the reference's property."""
+        return self.sample((self.n_test_set_samples,))
+
+    def expectation_function(self, x: torch.Tensor) -> torch.Tensor:
+        """The reference's quadratic test function (x+s)^T A (x+s) + b^T (x+s) with s = 2 randn(d),
+        A = 2 rand(d,d), b = rand(d) drawn after seeding with 0 -- here from a local generator, so
+        the values are the reference's but the global RNG is left alone."""
+        if self._quad_tables is None or self._quad_tables[0].shape[0] != x.shape[-1]:
+            g = torch.Generator().manual_seed(0)
+            d = x.shape[-1]
+            self._quad_tables = (2 * torch.randn(d, generator=g), 2 * torch.rand((d, d), generator=g),
+                                 torch.rand(d, generator=g))
+        s, A, b = (t.to(x) for t in self._quad_tables)
+        x = x + s
+        return torch.einsum("bi,ij,bj->b", x, A, x) + torch.einsum("i,bi->b", b, x)
+
+    @property
+    def true_expectation(self) -> torch.Tensor:
+        if self._true_expectation is None:
+            x = self.distribution.sample((self.true_expectation_estimation_n_samples,))
+            self._true_expectation = torch.mean(self.expectation_function(x))
+        return self._true_expectation
+
+    def evaluate_expectation(self, samples: torch.Tensor, log_w: torch.Tensor) -> torch.Tensor:
+        weights = torch.softmax(log_w, dim=-1)
+        estimate = weights @ self.expectation_function(samples)
+        truth = self.true_expectation.to(estimate.device)
+        return (estimate - truth) / truth
+
+    def performance_metrics(self, samples: torch.Tensor, log_w: torch.Tensor, log_q_fn=None,
+                            batch_size: Optional[int] = None):
+        bias_normed = self.evaluate_expectation(samples, log_w)
+        bias_no_correction = self.evaluate_expectation(samples, torch.ones_like(log_w))
+        if not log_q_fn:
+            return {"bias_normed": bias_normed.cpu().item(),
+                    "bias_no_correction": torch.abs(bias_no_correction).cpu().item()}
+        log_q_test = log_q_fn(self.test_set)            # (two different test sets: reference quirk)
+        log_p_test = self.log_prob(self.test_set)
+        ratio = log_p_test - log_q_test
+        return {"test_set_mean_log_prob": torch.mean(log_q_test).cpu().item(),
+                "bias_normed": torch.abs(bias_normed).cpu().item(),
+                "bias_no_correction": torch.abs(bias_no_correction).cpu().item(),
+                "ess_over_p": (1 / torch.mean(torch.exp(ratio))).detach().cpu().item(),
+                "kl_forward": torch.mean(ratio).detach().cpu().item()}
 
 
 class DiagGaussianTarget(GMM):

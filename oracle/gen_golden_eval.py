@@ -70,6 +70,49 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "eval_manywell.pt")
     torch.save(fixture, out)
     print(f"[gen_golden_eval] {checks} checks against the reference passed; wrote {out}")
+    gmm_checks()
+
+
+def gmm_checks():
+    """GMM target (gmm.py:71-99, numerical.py:8-60): quadratic test function, importance-weighted
+    bias metrics, and the model-density branch with callables standing in for the densities."""
+    from fab.target_distributions.gmm import GMM as Ref
+    from fab.utils.numerical import quadratic_function as ref_quad
+    from oracle import eval_gmm as eg
+    checks, fixture = 0, {}
+    for dim, n_mixes, loc in ((2, 4, 8.0), (3, 7, 5.0)):
+        torch.manual_seed(dim)
+        ref = Ref(dim=dim, n_mixes=n_mixes, loc_scaling=loc, log_var_scaling=1.0, use_gpu=False,
+                  true_expectation_estimation_n_samples=int(1e5))
+        g = torch.Generator().manual_seed(50 + dim)
+        x = torch.randn(3000, dim, generator=g) * loc
+        log_w = torch.randn(3000, generator=g) * 2
+        assert torch.equal(ref_quad(x), eg.quadratic_function(x)), "quadratic function"
+        checks += 1
+        m_ref = ref.performance_metrics(x, log_w)
+        assert m_ref == eg.performance_metrics(x, log_w, ref.true_expectation), "metrics without q"
+        checks += 1
+        log_q = lambda z: std_normal_log_prob(z / loc) - z.shape[-1] * math.log(loc)
+        torch.manual_seed(900 + dim)
+        m_q_ref = ref.performance_metrics(x, log_w, log_q)
+        torch.manual_seed(900 + dim)
+        m_q = eg.performance_metrics(x, log_w, ref.true_expectation, log_q, ref.log_prob,
+                                     lambda: ref.sample((ref.n_test_set_samples,)))
+        # the reference re-seeds the global RNG inside quadratic_function (`torch.seed()`,
+        # numerical.py:40), so its two test sets cannot be reproduced by seeding: the bias terms
+        # must agree exactly, the test-set statistics (1000 fresh samples each) only statistically
+        for k in ("bias_normed", "bias_no_correction"):
+            assert m_q_ref[k] == m_q[k], (k, m_q_ref, m_q)
+        for k, tol in (("test_set_mean_log_prob", 0.2), ("kl_forward", 0.2)):
+            assert abs(m_q_ref[k] - m_q[k]) < tol, (k, m_q_ref, m_q)
+        assert 0.5 < m_q_ref["ess_over_p"] / m_q["ess_over_p"] < 2.0 and set(m_q_ref) == set(m_q)
+        checks += 1
+        fixture[dim] = dict(ctor_seed=dim, n_mixes=n_mixes, loc_scaling=loc, locs=ref.locs.clone(),
+                            true_expectation=ref.true_expectation.clone(), x=x, log_w=log_w,
+                            quad=ref_quad(x), metrics_no_q=m_ref, metrics_q=m_q_ref, q_seed=900 + dim)
+    out = os.path.join(ROOT, "tests", "golden", "eval_gmm.pt")
+    torch.save(fixture, out)
+    print(f"[gen_golden_eval] GMM: {checks} checks against the reference passed; wrote {out}")
 
 
 if __name__ == "__main__":
