@@ -179,15 +179,16 @@ k_ais_init(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
 
 // ---------------------------------------------------------------------------------------------
 // deterministic cross-CTA reduction: every CTA deposits `NV` floats, the last one to arrive sums
-// them in block order.  Workspace: float partial[grid][NV] followed by one uint32 counter, which
-// must be 0 on entry and is reset to 0 on exit.
+// them in block order.  Workspace: one uint32 arrival counter in the FIRST 16 bytes (a fixed place:
+// it must not move when the grid size changes between launches that share a workspace), then
+// float partial[grid][NV].  The counter must be 0 on entry and is reset to 0 on exit.
 // Returns true (block-uniform) in the last CTA, with totals[NV] (shared) filled.
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 __device__ bool grid_reduce_last(const float* mine /*shared[NV]*/, float* ws, float* totals) {
     __shared__ int s_last;
-    float* partial = ws;
-    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)gridDim.x * NV);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    float* partial = ws + 4;
     if (threadIdx.x == 0) {
         for (int v = 0; v < NV; ++v) partial[(size_t)blockIdx.x * NV + v] = mine[v];
         __threadfence();
