@@ -102,7 +102,29 @@ SIGNATURES = {
     "fab_buffer_topk_workspace_bytes": (C.c_int64, [C.c_int64]),
     "fab_buffer_topk_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "fab_buffer_adjust_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
+    # row-tile engine (tcgen05 / TMEM / TMA)
+    "fab_umma_supported": (C.c_int, [C.POINTER(FlowDesc)]),
+    "fab_umma_blob_bytes": (C.c_int64, [C.POINTER(FlowDesc)]),
+    "fab_umma_plain_layout": (C.c_int, [C.POINTER(FlowDesc), C.POINTER(C.c_int64)]),
+    "fab_umma_pack_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, _P]),
+    "fab_umma_workspace_bytes": (C.c_int64, [C.POINTER(FlowDesc), C.c_int64]),
+    "fab_flow_logprob_grad_umma_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "fab_hmc_step_umma_f32": (C.c_int, [C.POINTER(FlowDesc), _P, C.POINTER(TargetDesc), HmcState,
+                                        HmcArgs, PointPtrs, PointPtrs, PointPtrs, _P, _P, _P, _P, _P,
+                                        _P, C.c_int64, _P]),
 }
+
+
+def engine_choice() -> str:
+    """FAB_ENGINE = auto (default) | rowtile | warp.  `auto` takes the row-tile (tcgen05) engine
+    when the flow shape is covered and the batch holds at least FAB_ROWTILE_MIN_N particles
+    (default 1024: below that the 128-row tiles leave most SMs idle and the warp-level engine,
+    which spreads <= 16 particles per SM, is faster)."""
+    return os.environ.get("FAB_ENGINE", "auto")
+
+
+def rowtile_min_n() -> int:
+    return int(os.environ.get("FAB_ROWTILE_MIN_N", "1024"))
 
 _lib: Optional[C.CDLL] = None
 

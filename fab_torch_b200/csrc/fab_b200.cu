@@ -1,5 +1,6 @@
 // libfab_b200.so -- C ABI (include/fab_b200.h) over the sm_100a kernels.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +10,7 @@
 #include "tile_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "buffer_kernels.cuh"
+#include "host_util.h"
 
 namespace {
 
@@ -83,6 +85,10 @@ inline int sample_state(int, int) { return 16; }
     }
 
 }  // namespace
+
+int fab_fail(int code, const std::string& msg) { return fail(code, msg); }
+int fab_cuda_fail(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+bool fab_flow_ok(const fab_flow_desc* f) { return flow_ok(f); }
 
 extern "C" {
 
@@ -532,3 +538,5 @@ int fab_debug_cta_cycles(unsigned long long* out1024, unsigned int* smid1024) {
 #endif
 
 }  // extern "C"
+
+bool fab_target_ok(const fab_target_desc* t) { return target_ok(t); }

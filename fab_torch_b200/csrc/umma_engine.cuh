@@ -1,0 +1,990 @@
+// Row-tile engine: RealNVP log-density + input-gradient and the fused HMC outer step on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory, weights staged into
+// shared memory by the TMA engine).  Used for batches that fill 128-row tiles; smaller batches
+// and shapes this engine does not cover stay on the warp-level engine (tile_kernels.cuh).
+//
+// Decomposition (measured choices: profiles/r02_mb_umma_*.log)
+//   * A CTA PAIR (cluster of 2, tcgen05 cta_group::2, instruction M = 128) carries 128 particles,
+//     64 per CTA.  cta_group::2 runs the 64-row half tile of each SM at the full tensor rate
+//     (8172 of 8192 FLOP/cycle/SM measured) and each CTA stages only half of every weight matrix.
+//   * fp32-grade GEMMs from f16 tensor-core products: every operand is split as v*s = hi + lo
+//     (f16 each, s a power of two -- per particle row for activations, per matrix for weights --
+//     chosen so that the largest element sits in [2^13, 2^14)); D = hi*hi + (lo*hi + hi*lo), the
+//     cross terms in their own accumulator, fp32 accumulation in tensor memory.  The tensor core
+//     truncates each accumulation toward zero (measured): the mean shrink, 1.67e-8 per
+//     accumulation of the hi*hi chain for mixed-sign data, is folded into the un-scaling factor.
+//   * Thread (row r, column group q = 0..3) of the 8 compute warps owns columns [q*N/4, (q+1)*N/4)
+//     of every activation of particle r for the whole kernel: the running latent, the momentum and
+//     the gradients live in its registers; only MMA operands pass through shared memory.
+//   * Bias vectors ride in the GEMMs: each biased operand has one extra k-step whose first column
+//     holds the row scale s ("ones" column after un-scaling) and meets the bias row of the weights.
+//   * Saved-for-backward state: (y2, exp(-scale)) of every coupling layer in the 160 tensor-memory
+//     columns the accumulators do not use; ReLU masks (80 bits per thread and GEMM) in a caller-
+//     owned scratch buffer (L2 resident).
+//
+// Warp roles (320 threads): warps 0-7 compute (epilogues, coupling, leapfrog, accept), warp 8
+// lane 0 issues the MMAs (leader CTA) or relays "my half of the weights has landed" to the leader
+// (peer CTA), warp 9 lane 0 streams weight stages global -> shared with cp.async.bulk.
+#pragma once
+#include <cuda_fp16.h>
+#include "umma.cuh"
+#include "common.cuh"
+#include "target_tile.cuh"
+
+#define UE_ROWS 64
+#define UE_THREADS 320
+#define UE_CTHREADS 256
+#define UE_STAGE_BYTES 22528      // two k-steps of the widest operand (352 rows x 32 bytes each)
+#define UE_NSTAGE 4
+#define UE_ACC_COLS 352          // accumulator columns; [352, 512) hold the saved coupling state
+#define UE_DQ 8                  // columns of a d-wide vector per thread (d = 32)
+#define UE_TRUNC_PER_ACC 1.67e-8f
+
+// One operand-matrix type of a layer (host-built, include/fab_b200.h documents the blob).
+struct UType {
+    int KS;            // k-steps of 16 (incl. the bias step)
+    int ksps;          // k-steps per pipeline stage
+    int R;             // weight rows per CTA and 16-byte k-chunk ( = N: hi and lo rows of N/2 outputs)
+    int nbh;           // accumulator columns per block: wide N/4, narrow N/2
+    int wide;          // 1: two column blocks x three MMAs per k-step; 0: narrow "concat" form
+    int a_off, a_lo;   // shared-memory byte offset of the A operand (hi plane), distance to the lo plane
+    int dcol;          // first accumulator column
+    uint32_t idesc_a, idesc_b;
+    long long blob_off;    // byte offset inside a layer block (rank 0; rank 1 follows at KS*R*32)
+    int Kreal, N;      // logical K (without bias step) and N
+    int bias;          // 1: a bias row follows the Kreal weight rows
+    long long plain_off, plain_bias_off;   // float offsets inside a layer block of the plain buffer
+};
+
+struct ULayout {
+    int d, W, K, WQ;
+    UType t[7];
+    long long blob_bytes, off_layers, layer_bytes;     // blob: [scalars][layer blocks]
+    int o_loc, o_lsc, o_scal;                           // float offsets in the scalar block; scal[K][8]
+    long long plain_floats, plain_layer_floats, plain_off_layers;
+    long long plain_logs_off;                           // float offset of sum(log_S) inside a plain layer block
+    int s_h, s_z, s_par, s_gv, s_ring, s_ex, s_bar, smem_bytes;
+    int hplane, zplane, pplane;
+    float dl[8];     // truncation compensation: [0] v columns of type 0, [1] h1pre of type 0, [2..7] types 1..6
+};
+
+__host__ inline bool umma_supported(int d, int W, int K) { return d == 32 && W % 64 == 0 && W >= 64 && W <= 320 && K >= 1 && K <= 10; }
+
+__host__ inline ULayout make_ulayout(int d, int W, int K) {
+    ULayout L{};
+    L.d = d; L.W = W; L.K = K; L.WQ = W / 4;
+    const int hplane = UE_ROWS * (W + 16) * 2, zplane = UE_ROWS * (d + 16) * 2, pplane = UE_ROWS * d * 2;
+    L.hplane = hplane; L.zplane = zplane; L.pplane = pplane;
+    int o = 0;
+    L.s_h = o; o += 2 * hplane;
+    L.s_z = o; o += 2 * zplane;
+    L.s_par = o; o += 2 * pplane;
+    L.s_gv = o; o += 2 * pplane;
+    o = (o + 127) & ~127;
+    L.s_ring = o; o += UE_NSTAGE * UE_STAGE_BYTES;
+    L.s_ex = o; o += 4 * 4 * UE_ROWS * 4 * 2;     // exchange buffers: 4 rotating x [2 values][4 groups][64 rows]
+    L.s_bar = o; o += (2 * UE_NSTAGE + 2) * 8 + 16;
+    L.smem_bytes = o;
+    auto set = [&](int i, int Kreal, int N, int bias, int wide, int a_off, int a_lo, int dcol) {
+        UType& t = L.t[i];
+        t.Kreal = Kreal; t.N = N; t.bias = bias; t.wide = wide;
+        t.KS = Kreal / 16 + (bias ? 1 : 0);
+        t.R = N;
+        t.nbh = wide ? N / 4 : N / 2;
+        t.ksps = UE_STAGE_BYTES / (t.R * 32);
+        if (t.ksps > t.KS) t.ksps = t.KS;
+        t.a_off = a_off; t.a_lo = a_lo; t.dcol = dcol;
+        t.idesc_a = umma::instr_desc(umma::FMT_F16, 128, wide ? N / 2 : 2 * N);
+        t.idesc_b = umma::instr_desc(umma::FMT_F16, 128, wide ? N / 2 : N);
+    };
+    set(0, d, d + W, 1, 1, L.s_z, zplane, 0);        // z -> [v | h1pre]
+    set(1, W, W, 1, 1, L.s_h, hplane, 0);            // h1 -> h2pre
+    set(2, W, d, 1, 0, L.s_h, hplane, 0);            // h2 -> [shift | scale]
+    set(3, d, W, 0, 1, L.s_par, pplane, 0);          // gparam -> gh2
+    set(4, W, W, 0, 1, L.s_h, hplane, 0);            // gh2 -> gh1
+    set(5, W, d, 0, 0, L.s_h, hplane, 0);            // gh1 -> g (first part)
+    set(6, d, d, 0, 0, L.s_gv, pplane, d);           // gv  -> g (second part)
+    long long bo = 0, po = 0;
+    for (int i = 0; i < 7; ++i) {
+        UType& t = L.t[i];
+        t.blob_off = bo; bo += 2LL * t.KS * t.R * 32;
+        t.plain_off = po; po += (long long)t.Kreal * t.N;
+        t.plain_bias_off = po; if (t.bias) po += t.N;
+    }
+    L.plain_logs_off = po; po += 4;
+    L.layer_bytes = bo; L.plain_layer_floats = po;
+    L.o_loc = 0; L.o_lsc = d; L.o_scal = 2 * d;
+    L.off_layers = ((2 * d + 8 * K) * 4 + 127) & ~127;
+    L.blob_bytes = L.off_layers + L.layer_bytes * K;
+    L.plain_off_layers = 2 * d;
+    L.plain_floats = L.plain_off_layers + L.plain_layer_floats * K;
+    // mean relative shrink of a chain of n truncating accumulations at ~final magnitude: measured
+    // 1.67e-8 n for long mixed-sign chains (profiles/r02_mb_umma_layout_rounding_split.log); the
+    // v = z @ Wmix columns see no bias row, i.e. one accumulation less
+    L.dl[0] = 4.5e-8f;     // calibrated on log q of a 10-layer flow (one FMA rounds up for ~60 % of the mantissas)
+    L.dl[1] = UE_TRUNC_PER_ACC * (float)L.t[0].KS;
+    for (int i = 1; i < 7; ++i) L.dl[1 + i] = UE_TRUNC_PER_ACC * (float)L.t[i].KS;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: plain fp32 matrices M[k][n] (+ bias rows) -> per-rank f16 hi/lo stage images
+// ---------------------------------------------------------------------------------------------
+// one block per (layer, type): s_w = 2^e with max|M|,|bias| * s_w in [2^13, 2^14); writes
+// scal[layer][type] = (1 / s_w) * (1 + UE_TRUNC_PER_ACC * KS) and scal[layer][7] = sum(log_S).
+__global__ void k_umma_scales(ULayout L, const float* __restrict__ plain, float* __restrict__ blob_f) {
+    const int layer = blockIdx.x / 7, ti = blockIdx.x % 7;
+    const UType& t = L.t[ti];
+    const float* M = plain + L.plain_off_layers + (size_t)layer * L.plain_layer_floats + t.plain_off;
+    const long long cnt = (long long)t.Kreal * t.N + (t.bias ? t.N : 0);
+    float m = 0.f;
+    for (long long i = threadIdx.x; i < cnt; i += blockDim.x) m = fmaxf(m, fabsf(M[i]));
+    __shared__ float red[32];
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+        int e = 0;
+        if (m > 0.f && m < CUDART_INF_F) { frexpf(m, &e); e = 14 - e; }
+        if (e > 30) e = 30;
+        if (e < -30) e = -30;
+        float* scal = blob_f + L.o_scal + (size_t)layer * 8;
+        scal[ti] = ldexpf(1.f, -e);
+        // the exponent itself, for the pack kernel (scratch behind the scalar table is not available:
+        // recover it there from scal by the same formula)
+        if (ti == 0) scal[7] = plain[L.plain_off_layers + (size_t)layer * L.plain_layer_floats + L.plain_logs_off];
+    }
+    if (blockIdx.x == 0)
+        for (int j = threadIdx.x; j < 2 * L.d; j += blockDim.x) blob_f[j] = plain[j];
+}
+
+// one thread per 16-byte chunk of the images: grid.x covers (layer, type, rank, chunk, row)
+__global__ void k_umma_pack(ULayout L, const float* __restrict__ plain, uint8_t* __restrict__ blob) {
+    const int layer = blockIdx.y, ti = blockIdx.z;
+    const UType& t = L.t[ti];
+    const long long per_rank = (long long)t.KS * 2 * t.R;          // chunks x rows
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * per_rank) return;
+    const int rank = (int)(idx / per_rank);
+    const long long rem = idx % per_rank;
+    const int c = (int)(rem / t.R), row = (int)(rem % t.R);
+    // row -> (part, output column n)
+    int part, n;
+    if (t.wide) {
+        const int g = row / (2 * t.nbh), r2 = row % (2 * t.nbh);
+        part = r2 / t.nbh;
+        const int i = r2 % t.nbh, q = 2 * g + rank;
+        if (ti == 0) n = i < L.WQ ? L.d + q * L.WQ + i : q * UE_DQ + (i - L.WQ);    // [h1pre cols | v cols]
+        else n = q * L.WQ + i;
+    } else {
+        part = row / t.nbh;
+        const int i = row % t.nbh;
+        n = i < UE_DQ ? rank * UE_DQ + i : L.d / 2 + rank * UE_DQ + (i - UE_DQ);
+    }
+    const float* blob_f = reinterpret_cast<const float*>(blob);
+    // s_w from the scale kernel's output scal = 1 / s_w
+    const float sc = blob_f[L.o_scal + (size_t)layer * 8 + ti];
+    const float sw = 1.f / sc;             // both powers of two
+    const float* M = plain + L.plain_off_layers + (size_t)layer * L.plain_layer_floats + t.plain_off;
+    const float* B = plain + L.plain_off_layers + (size_t)layer * L.plain_layer_floats + t.plain_bias_off;
+    __half out[8];
+    for (int j = 0; j < 8; ++j) {
+        const int k = 8 * c + j;
+        float v = 0.f;
+        if (k < t.Kreal) v = M[(size_t)k * t.N + n];
+        else if (k == t.Kreal && t.bias) v = B[n];
+        v *= sw;
+        const __half hi = __float2half_rn(v);
+        out[j] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    }
+    uint8_t* dst = blob + L.off_layers + (size_t)layer * L.layer_bytes + t.blob_off +
+                   (size_t)rank * t.KS * t.R * 32 + ((size_t)c * t.R + row) * 16;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+extern __shared__ __align__(1024) uint8_t ue_smem[];
+
+// -DUE_PROF: cycle counters of CTA 0 (compute warp 0 lane 0, the MMA issuer, the producer);
+// read back with fab_umma_prof_read.  0: compute waits for accumulators, 1: compute epilogue work,
+// 2: issuer waits for operands (aready), 3: issuer waits for weight stages, 4: issuer issues,
+// 5: producer waits for free slots, 6: compute barrier/exchange, 7: kernel total (compute warp 0)
+#ifdef UE_PROF
+__device__ unsigned long long g_ue_prof[16];
+#define UE_T0() const long long ue_t0_ = clock64()
+#define UE_ACC(id, cond) if (cond) atomicAdd(&g_ue_prof[id], (unsigned long long)(clock64() - ue_t0_))
+#else
+#define UE_T0()
+#define UE_ACC(id, cond)
+#endif
+
+// full[s]: stage s has landed -- in the leader CTA it counts two arrivals: its own producer's
+// expect_tx and the peer's relay (so the MMA issuer polls ONE barrier per stage: a try_wait costs
+// ~100 cycles of the single issuing thread even when the phase is already complete).
+struct UBars { uint64_t *full, *empty, *dfull, *aready; };
+__device__ __forceinline__ UBars ue_bars(const ULayout& L) {
+    uint64_t* b = reinterpret_cast<uint64_t*>(ue_smem + L.s_bar);
+    return {b, b + UE_NSTAGE, b + 2 * UE_NSTAGE, b + 2 * UE_NSTAGE + 1};
+}
+
+// The GEMM groups of one flow evaluation, in execution order.  f(layer, first type, last type).
+template <class F>
+__device__ __forceinline__ void ue_for_each_group(const ULayout& L, bool grad, F f) {
+    for (int k = L.K - 1; k >= 0; --k) { f(k, 0, 0); f(k, 1, 1); f(k, 2, 2); }
+    if (grad) for (int k = 0; k < L.K; ++k) { f(k, 3, 3); f(k, 4, 4); f(k, 5, 6); }
+}
+
+// warp 9 (warp-uniform loop, one elected lane issues): stream every weight stage of `n_evals` flow evaluations into the ring
+__device__ void ue_producer(const ULayout& L, const uint8_t* __restrict__ blob, uint32_t rank, int n_evals, bool grad) {
+    const UBars B = ue_bars(L);
+    const uint64_t pol = umma::l2_evict_last_policy();
+    uint32_t it = 0;
+    for (int ev = 0; ev < n_evals; ++ev)
+        ue_for_each_group(L, grad, [&](int k, int t0, int t1) {
+            for (int ti = t0; ti <= t1; ++ti) {
+                const UType& t = L.t[ti];
+                const uint8_t* src = blob + L.off_layers + (size_t)k * L.layer_bytes + t.blob_off + (size_t)rank * t.KS * t.R * 32;
+                for (int s0 = 0; s0 < t.KS; s0 += t.ksps) {
+                    const int cnt = min(t.ksps, t.KS - s0);
+                    const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
+                    { UE_T0(); umma::mbar_wait(B.empty + slot, par ^ 1); UE_ACC(5, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
+                    const uint32_t bytes = (uint32_t)cnt * t.R * 32;
+                    if (umma::elect_one()) {
+                        umma::mbar_expect_tx(B.full + slot, bytes);
+                        umma::bulk_g2s(ue_smem + L.s_ring + slot * UE_STAGE_BYTES, src + (size_t)s0 * t.R * 32, bytes, B.full + slot, pol);
+                    }
+                    __syncwarp();
+                    ++it;
+                }
+            }
+        });
+}
+
+// warp 8 of the peer CTA: tell the leader when this CTA's half of a stage has landed
+__device__ void ue_relay(const ULayout& L, int n_evals, bool grad) {
+    const UBars B = ue_bars(L);
+    uint32_t it = 0;
+    for (int ev = 0; ev < n_evals; ++ev)
+        ue_for_each_group(L, grad, [&](int, int t0, int t1) {
+            for (int ti = t0; ti <= t1; ++ti) {
+                const UType& t = L.t[ti];
+                for (int s0 = 0; s0 < t.KS; s0 += t.ksps) {
+                    const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
+                    umma::mbar_wait(B.full + slot, par);
+                    if (umma::elect_one()) umma::mbar_arrive_remote(B.full + slot, 0);
+                    __syncwarp();
+                    ++it;
+                }
+            }
+        });
+}
+
+// warp 8 of the leader CTA: issue the MMAs of the pair.  The whole warp runs the loop and one
+// elected lane issues, so that descriptors and addresses stay in uniform registers (a single-lane
+// code path costs ~45 cycles per tcgen05.mma in compiler-generated elect loops; uniform: 21-40,
+// profiles/r02_mb_umma_rates.log)
+__device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) {
+    const UBars B = ue_bars(L);
+    const uint32_t sbase = umma::smem_u32(ue_smem);
+    uint32_t it = 0, gi = 0;
+    for (int ev = 0; ev < n_evals; ++ev)
+        ue_for_each_group(L, grad, [&](int, int t0, int t1) {
+            { UE_T0(); umma::mbar_wait_cluster(B.aready, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
+            umma::tc_fence_after();
+            for (int ti = t0; ti <= t1; ++ti) {
+                const UType& t = L.t[ti];
+                const uint32_t lbo_b = (uint32_t)t.R * 16;
+                for (int s0 = 0; s0 < t.KS; s0 += t.ksps) {
+                    const int cnt = min(t.ksps, t.KS - s0);
+                    const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
+                    { UE_T0(); umma::mbar_wait_cluster(B.full + slot, par); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
+                    umma::tc_fence_after();
+                    UE_T0();
+                    // descriptors: high word constant (SBO = 128 B, version 1), low word = addr >> 4 | LBO >> 4 << 16
+                    const uint32_t sb = sbase + L.s_ring + slot * UE_STAGE_BYTES;
+                    const uint32_t dhi = (128u >> 4) | (1u << 14);
+                    const uint32_t alo = ((sbase + t.a_off) >> 4) | ((1024u >> 4) << 16), alo_d = (uint32_t)t.a_lo >> 4;
+                    const uint32_t blo = (sb >> 4) | ((lbo_b >> 4) << 16), kstr = (uint32_t)t.R * 2;   // 32 R bytes per k-step
+                    auto desc = [&](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
+                    const bool leader_lane = umma::elect_one();
+                    if (leader_lane)
+                    for (int j = 0; j < cnt; ++j) {
+                        const int ks = s0 + j;
+                        const uint64_t dah = desc(alo + ks * 128), dal = desc(alo + alo_d + ks * 128);
+                        const uint32_t bk = blo + (uint32_t)j * kstr;
+                        const bool acc = ks > 0;
+                        if (t.wide) {
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const uint64_t dbh = desc(bk + (uint32_t)(g * 2 * t.nbh)), dbl = desc(bk + (uint32_t)(g * 2 * t.nbh + t.nbh));
+                                const uint32_t dm = tmem + t.dcol + g * t.nbh, dx = dm + 2 * t.nbh;
+                                umma::mma_ss<2, true>(dx, dal, dbh, t.idesc_a, acc);
+                                umma::mma_ss<2, true>(dx, dah, dbl, t.idesc_a, true);
+                                umma::mma_ss<2, true>(dm, dah, dbh, t.idesc_a, acc);
+                            }
+                        } else {
+                            const uint64_t db = desc(bk);
+                            umma::mma_ss<2, true>(tmem + t.dcol, dah, db, t.idesc_a, acc);               // [hi*hi | hi*lo]
+                            umma::mma_ss<2, true>(tmem + t.dcol + t.nbh, dal, db, t.idesc_b, true);      // += lo*hi
+                        }
+                    }
+                    if (leader_lane) umma::mma_commit<2>(B.empty + slot, 3);
+                    __syncwarp();
+                    UE_ACC(4, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
+                    ++it;
+                }
+            }
+            if (umma::elect_one()) umma::mma_commit<2>(B.dfull, 3);
+            __syncwarp();
+            ++gi;
+        });
+}
+
+// ---- compute warps --------------------------------------------------------------------------------
+struct UCw {
+    int r, q, g, h;             // row, column group (2g + h), block, half
+    uint32_t tl;                // tensor-memory lane base of the warp << 16
+    uint32_t gi;                // GEMM groups consumed so far (phase of dfull)
+    uint32_t xb;                // rotating exchange buffer index
+    uint32_t tmem;
+    uint32_t rank;
+};
+
+__device__ __forceinline__ void ue_bar_compute() {
+    UE_T0();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    UE_ACC(6, blockIdx.x == 0 && threadIdx.x == 0);
+}
+
+__device__ __forceinline__ float* ue_exbuf(const ULayout& L, UCw& c) {
+    float* b = reinterpret_cast<float*>(ue_smem + L.s_ex) + (c.xb & 3) * (2 * 4 * UE_ROWS);
+    ++c.xb;
+    return b;
+}
+// max over the four threads of a row (two values at once)
+__device__ __forceinline__ void ue_row_max2(const ULayout& L, UCw& c, float& a, float& b) {
+    float* ex = ue_exbuf(L, c);
+    ex[c.q * UE_ROWS + c.r] = a;
+    ex[4 * UE_ROWS + c.q * UE_ROWS + c.r] = b;
+    ue_bar_compute();
+    a = fmaxf(fmaxf(ex[c.r], ex[UE_ROWS + c.r]), fmaxf(ex[2 * UE_ROWS + c.r], ex[3 * UE_ROWS + c.r]));
+    const float* e2 = ex + 4 * UE_ROWS;
+    b = fmaxf(fmaxf(e2[c.r], e2[UE_ROWS + c.r]), fmaxf(e2[2 * UE_ROWS + c.r], e2[3 * UE_ROWS + c.r]));
+}
+// sum over the four threads of a row in the canonical order q = 0, 1, 2, 3 (two values at once)
+__device__ __forceinline__ void ue_row_sum2(const ULayout& L, UCw& c, float& a, float& b) {
+    float* ex = ue_exbuf(L, c);
+    ex[c.q * UE_ROWS + c.r] = a;
+    ex[4 * UE_ROWS + c.q * UE_ROWS + c.r] = b;
+    ue_bar_compute();
+    a = ((ex[c.r] + ex[UE_ROWS + c.r]) + ex[2 * UE_ROWS + c.r]) + ex[3 * UE_ROWS + c.r];
+    const float* e2 = ex + 4 * UE_ROWS;
+    b = ((e2[c.r] + e2[UE_ROWS + c.r]) + e2[2 * UE_ROWS + c.r]) + e2[3 * UE_ROWS + c.r];
+}
+// power-of-two operand scale: row maximum -> [2^13, 2^14).  BIASED operands carry s itself as an f16
+// number (the "ones" column), so s <= 2^15 there (rows whose maximum is below 2^-2 keep a smaller
+// scaled maximum, still far above the f16 subnormals); a row maximum above 2^38 makes the ones
+// column underflow, i.e. drops a bias that is < 1e-11 of the row.  Gradient operands are un-biased
+// and take the full exponent range (tiny or huge gradient rows keep 22 significant bits).
+template <bool BIASED>
+__device__ __forceinline__ void ue_scale_of(float m, float& s, float& inv_s) {
+    int es = 0;
+    if (m > 0.f) {
+        const int E = (int)((__float_as_uint(m) >> 23) & 0xffu);      // m in [2^(E-127), 2^(E-126))
+        es = 13 - (E - 127);
+        if (BIASED && es > 15) es = 15;
+        if (es > 120) es = 120;
+        if (es < -120) es = -120;
+    }
+    s = __uint_as_float((uint32_t)(es + 127) << 23);
+    inv_s = __uint_as_float((uint32_t)(127 - es) << 23);
+}
+// split eight scaled values into f16 hi / lo and store them as one 16-byte k-chunk of row r
+__device__ __forceinline__ void ue_store_chunk(uint8_t* hi_plane, int a_lo, int chunk, int r, const float (&v)[8]) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    uint8_t* p = hi_plane + (size_t)chunk * (UE_ROWS * 16) + r * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(p + a_lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+// the "ones" column of a biased operand: first element of k-chunk `chunk` = s (rest of the chunk
+// and the lo plane stay zero from initialisation)
+__device__ __forceinline__ void ue_store_one(uint8_t* hi_plane, int chunk, int r, float s) {
+    *reinterpret_cast<__half*>(hi_plane + (size_t)chunk * (UE_ROWS * 16) + r * 16) = __float2half_rn(s);
+}
+// operand complete: make it visible to the tensor core and release the MMA issuer (one arrive per warp)
+__device__ __forceinline__ void ue_operand_ready(const ULayout& L) {
+    umma::fence_proxy_async();
+    umma::tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) umma::mbar_arrive_remote(ue_bars(L).aready, 0);
+}
+// wait for the accumulators of the next GEMM group
+__device__ __forceinline__ void ue_wait_acc(const ULayout& L, UCw& c) {
+    { UE_T0(); umma::mbar_wait(ue_bars(L).dfull, c.gi & 1); UE_ACC(0, blockIdx.x == 0 && threadIdx.x == 0); }
+    ++c.gi;
+    umma::tc_fence_after();
+}
+// v = (main + cross) (1 + dl) cf: dl compensates the mean shrink of the truncating accumulation
+// (one FMA: c + c*dl is rounded once, so a correction below one ulp is applied "on average");
+// cf is a power of two (exact).
+__device__ __forceinline__ void ue_acc16(uint32_t ta_main, uint32_t ta_cross, float cf, float dl, float (&v)[16]) {
+    // (x8 loads: the thread's first column is a multiple of 8, not of 16)
+    uint32_t a0[8], a1[8], b0[8], b1[8];
+    umma::tmem_ld8(ta_main, a0);
+    umma::tmem_ld8(ta_main + 8, a1);
+    umma::tmem_ld8(ta_cross, b0);
+    umma::tmem_ld8(ta_cross + 8, b1);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float t0 = __uint_as_float(a0[i]) + __uint_as_float(b0[i]), t1 = __uint_as_float(a1[i]) + __uint_as_float(b1[i]);
+        v[i] = fmaf(t0, dl, t0) * cf;
+        v[8 + i] = fmaf(t1, dl, t1) * cf;
+    }
+}
+__device__ __forceinline__ void ue_acc8(uint32_t ta_main, uint32_t ta_cross, float cf, float dl, float (&v)[8]) {
+    uint32_t a[8], b[8];
+    umma::tmem_ld8(ta_main, a);
+    umma::tmem_ld8(ta_cross, b);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float t = __uint_as_float(a[i]) + __uint_as_float(b[i]); v[i] = fmaf(t, dl, t) * cf; }
+}
+
+// Epilogue of a wide GEMM into the hidden operand (in place): the thread's WQ columns, two passes
+// over tensor memory (row maximum, then scale / split / store).
+//   FWD:  h = relu(acc)   and the ReLU mask of the thread's columns is produced (mask[] out)
+//   !FWD: h = mask ? acc : 0                                           (mask[] in)
+// ta_main / ta_cross: tensor-memory addresses (lane base included) of the thread's first column.
+// 16 consecutive accumulator columns of the thread's lane (no wait).  The thread's first column is a
+// multiple of 8; -DUE_LD16 uses one x16 load (tensor-memory loads need no alignment beyond the
+// 32-bit column: profiles/r02_mb_umma_rates.log "ldalign"), otherwise two x8 loads.
+__device__ __forceinline__ void ue_ld16(uint32_t ta, uint32_t (&v)[16]) {
+#ifdef UE_LD16
+    umma::tmem_ld16(ta, v);
+#else
+    uint32_t a[8], b[8];
+    umma::tmem_ld8(ta, a);
+    umma::tmem_ld8(ta + 8, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = a[i]; v[8 + i] = b[i]; }
+#endif
+}
+
+// NCH = WQ / 16: chunks of 16 hidden columns per thread (compile time: the register arrays below
+// must be statically indexed)
+template <bool FWD, int NCH>
+__device__ __forceinline__ void ue_epi_hidden(const ULayout& L, UCw& c, uint32_t ta_main, uint32_t ta_cross, float cf, float dl,
+                                              uint32_t (&mask)[3], bool bias_col, float& inv_s_out) {
+    // pass 1: row maximum from the hi*hi accumulator alone (the cross terms are ~2^-11 of it; the
+    // scale only has to put the largest element near 2^13, with a factor 4 of headroom below the
+    // f16 maximum), un-scaled: max(relu(v)) = max(0, max v), cf > 0.  All loads first, one wait.
+    float m = 0.f, dummy = 0.f;
+    {
+        uint32_t a[NCH][16];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) ue_ld16(ta_main + 16 * j, a[j]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const uint32_t mw = FWD ? 0u : mask[j >> 1] >> (16 * (j & 1));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (FWD) m = fmaxf(m, __uint_as_float(a[j][i]));
+                else m = fmaxf(m, ((mw >> i) & 1u) ? fabsf(__uint_as_float(a[j][i])) : 0.f);
+            }
+        }
+    }
+    m *= cf;
+    ue_row_max2(L, c, m, dummy);
+    float s, inv_s;
+    ue_scale_of<FWD>(m, s, inv_s);          // forward operands are the biased ones
+    inv_s_out = inv_s;
+    const float sc = cf * s;                 // un-scale and re-scale in one (s is a power of two)
+    uint8_t* hp = ue_smem + L.s_h;
+    uint32_t nm[3] = {0u, 0u, 0u};
+    // pass 2 in batches of two chunks: loads of a batch first, one wait, then scale / split / store
+#pragma unroll
+    for (int j0 = 0; j0 < NCH; j0 += 2) {
+        uint32_t a[2][16], b[2][16];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) if (j0 + jj < NCH) {
+            ue_ld16(ta_main + 16 * (j0 + jj), a[jj]);
+            ue_ld16(ta_cross + 16 * (j0 + jj), b[jj]);
+        }
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) if (j0 + jj < NCH) {
+            const int j = j0 + jj;
+            const uint32_t mw = FWD ? 0u : mask[j >> 1] >> (16 * (j & 1));
+            uint32_t bits = 0;
+            float lo8[8], hi8[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = __uint_as_float(a[jj][i]) + __uint_as_float(b[jj][i]);
+                const float v = fmaf(t, dl, t) * sc;
+                float hv;
+                if (FWD) { const bool on = v > 0.f; bits |= (on ? 1u : 0u) << i; hv = on ? v : 0.f; }
+                else hv = ((mw >> i) & 1u) ? v : 0.f;
+                if (i < 8) lo8[i] = hv; else hi8[i - 8] = hv;
+            }
+            if (FWD) nm[j >> 1] |= bits << (16 * (j & 1));
+            const int chunk = (c.q * L.WQ) / 8 + 2 * j;
+            ue_store_chunk(hp, L.hplane, chunk, c.r, lo8);
+            ue_store_chunk(hp, L.hplane, chunk + 1, c.r, hi8);
+        }
+    }
+    if (FWD) { mask[0] = nm[0]; mask[1] = nm[1]; mask[2] = nm[2]; }
+    if (bias_col && c.q == 0) ue_store_one(hp, L.W / 8, c.r, s);
+}
+
+// ReLU-mask scratch: word w of (layer, which, group q) of global row `grow`
+__device__ __forceinline__ uint32_t* ue_mask_ptr(uint32_t* scratch, long long n_stride, int layer, int which, int q, long long grow) {
+    return scratch + ((size_t)((layer * 2 + which) * 4 + q) * 3) * n_stride + grow;
+}
+
+// d log N(z)/dz seed, log q pieces etc. are produced here.  On entry zc[] holds the thread's 8
+// columns of x; on exit (GRAD) gs[] holds d log q / dx of those columns; returns log q of the row
+// (identical in the four threads of the row).
+template <bool GRAD, int NCH>
+__device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const float* __restrict__ blob_f,
+                                              uint32_t* mscratch, long long n_stride, long long grow,
+                                              float (&zc)[UE_DQ], float (&gs)[UE_DQ]) {
+    uint8_t* const zp = ue_smem + L.s_z;
+    const float* scal = blob_f + L.o_scal;
+    float inv_s_z, inv_s_h = 1.f;
+    // x -> z operand
+    {
+        float m = 0.f, dummy = 0.f;
+#pragma unroll
+        for (int i = 0; i < UE_DQ; ++i) m = fmaxf(m, fabsf(zc[i]));
+        ue_row_max2(L, c, m, dummy);
+        float s;
+        ue_scale_of<true>(m, s, inv_s_z);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = zc[i] * s;
+        ue_store_chunk(zp, L.zplane, c.q, c.r, v);
+        if (c.q == 0) ue_store_one(zp, L.d / 8, c.r, s);
+        ue_operand_ready(L);
+    }
+    float sacc = 0.f;
+    const uint32_t tl = c.tmem + c.tl;
+    for (int k = L.K - 1; k >= 0; --k) {
+        float vreg[UE_DQ];
+        uint32_t mask[3];
+        // ---- G1: [v | h1pre] ---------------------------------------------------------------
+        {
+            const UType& t = L.t[0];
+            const float cf = inv_s_z * __ldg(scal + k * 8 + 0);
+            ue_wait_acc(L, c);
+            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
+            ue_acc8(tm + L.WQ, tx + L.WQ, cf, L.dl[0], vreg);
+            ue_epi_hidden<true, NCH>(L, c, tm, tx, cf, L.dl[1], mask, true, inv_s_h);
+            if (GRAD)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) ue_mask_ptr(mscratch, n_stride, k, 0, c.q, grow)[(size_t)w * n_stride] = mask[w];
+            ue_operand_ready(L);
+        }
+        // ---- G2: h2pre -----------------------------------------------------------------------
+        {
+            const UType& t = L.t[1];
+            const float cf = inv_s_h * __ldg(scal + k * 8 + 1);
+            ue_wait_acc(L, c);
+            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
+            ue_epi_hidden<true, NCH>(L, c, tm, tx, cf, L.dl[2], mask, true, inv_s_h);
+            if (GRAD)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) ue_mask_ptr(mscratch, n_stride, k, 1, c.q, grow)[(size_t)w * n_stride] = mask[w];
+            ue_operand_ready(L);
+        }
+        // ---- G3: [shift | scale] of the thread's transformed columns, coupling inverse -------------
+        {
+            const UType& t = L.t[2];
+            const float cf = inv_s_h * __ldg(scal + k * 8 + 2);
+            ue_wait_acc(L, c);
+            if (c.g == 1) {
+                float p[16];
+                ue_acc16(tl + t.dcol, tl + t.dcol + t.nbh, cf, L.dl[3], p);
+                uint32_t sv[16];
+#pragma unroll
+                for (int i = 0; i < UE_DQ; ++i) {
+                    const float shift = p[i], scale = p[UE_DQ + i];
+                    const float es = expf(-scale);
+                    const float y2 = (vreg[i] - shift) * es;
+                    zc[i] = y2;
+                    sacc += scale;
+                    sv[i] = __float_as_uint(y2);
+                    sv[UE_DQ + i] = __float_as_uint(es);
+                }
+                if (GRAD) { umma::tmem_st16(tl + UE_ACC_COLS + 16 * k, sv); umma::tmem_st_wait(); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < UE_DQ; ++i) zc[i] = vreg[i];
+            }
+            if (k > 0) {          // next layer's z operand
+                float m = 0.f, dummy = 0.f;
+#pragma unroll
+                for (int i = 0; i < UE_DQ; ++i) m = fmaxf(m, fabsf(zc[i]));
+                ue_row_max2(L, c, m, dummy);
+                float s;
+                ue_scale_of<true>(m, s, inv_s_z);
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = zc[i] * s;
+                ue_store_chunk(zp, L.zplane, c.q, c.r, v);
+                if (c.q == 0) ue_store_one(zp, L.d / 8, c.r, s);
+                ue_operand_ready(L);
+            }
+        }
+    }
+    // ---- base Gaussian -------------------------------------------------------------------------
+    float gpart = 0.f;
+#pragma unroll
+    for (int i = 0; i < UE_DQ; ++i) {
+        const int j = UE_DQ * c.q + i;
+        const float lsc = __ldg(blob_f + L.o_lsc + j), inv = expf(-lsc);
+        const float u = (zc[i] - __ldg(blob_f + L.o_loc + j)) * inv;
+        gpart += lsc + 0.5f * u * u;
+        gs[i] = -u * inv;
+    }
+    ue_row_sum2(L, c, gpart, sacc);
+    float logs = 0.f;
+    for (int k = 0; k < L.K; ++k) logs += __ldg(scal + k * 8 + 7);
+    const float lq = logs + (-0.5f * (float)L.d * 1.8378770664093453f - (gpart + sacc));
+    if (!GRAD) return lq;
+    // ---- input-gradient sweep ---------------------------------------------------------------------
+    uint8_t* const pp = ue_smem + L.s_par;
+    uint8_t* const gp = ue_smem + L.s_gv;
+    for (int k = 0; k < L.K; ++k) {
+        float inv_s_par, inv_s_gv;
+        // coupling backward: gparam and gv operands
+        {
+            float gpar[16], gv[UE_DQ];
+            float ma = 0.f, mb = 0.f;
+            if (c.g == 1) {
+                uint32_t sv[16];
+                umma::tmem_ld16(tl + UE_ACC_COLS + 16 * k, sv);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < UE_DQ; ++i) {
+                    const float y2 = __uint_as_float(sv[i]), es = __uint_as_float(sv[UE_DQ + i]);
+                    const float g2 = gs[i];
+                    const float gv2 = g2 * es;
+                    gpar[i] = -gv2;
+                    gpar[UE_DQ + i] = -g2 * y2 - 1.0f;
+                    gv[i] = gv2;
+                    ma = fmaxf(ma, fmaxf(fabsf(gpar[i]), fabsf(gpar[UE_DQ + i])));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < UE_DQ; ++i) gv[i] = gs[i];
+            }
+#pragma unroll
+            for (int i = 0; i < UE_DQ; ++i) mb = fmaxf(mb, fabsf(gv[i]));
+            ue_row_max2(L, c, ma, mb);
+            float sa, sb;
+            ue_scale_of<false>(ma, sa, inv_s_par);
+            ue_scale_of<false>(mb, sb, inv_s_gv);
+            if (c.g == 1) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gpar[i] * sa;
+                ue_store_chunk(pp, L.pplane, c.h, c.r, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gpar[UE_DQ + i] * sa;
+                ue_store_chunk(pp, L.pplane, 2 + c.h, c.r, v);
+            }
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = gv[i] * sb;
+            ue_store_chunk(gp, L.pplane, c.q, c.r, v);
+            ue_operand_ready(L);
+        }
+        uint32_t mask[3];
+        // ---- G3T: gh2 = (gparam @ W3) * m2 ---------------------------------------------------
+        {
+            const UType& t = L.t[3];
+            const float cf = inv_s_par * __ldg(scal + k * 8 + 3);
+#pragma unroll
+            for (int w = 0; w < 3; ++w) mask[w] = ue_mask_ptr(mscratch, n_stride, k, 1, c.q, grow)[(size_t)w * n_stride];
+            ue_wait_acc(L, c);
+            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
+            ue_epi_hidden<false, NCH>(L, c, tm, tx, cf, L.dl[4], mask, false, inv_s_h);
+            ue_operand_ready(L);
+        }
+        // ---- G2T: gh1 = (gh2 @ W2) * m1 ------------------------------------------------------
+        {
+            const UType& t = L.t[4];
+            const float cf = inv_s_h * __ldg(scal + k * 8 + 4);
+#pragma unroll
+            for (int w = 0; w < 3; ++w) mask[w] = ue_mask_ptr(mscratch, n_stride, k, 0, c.q, grow)[(size_t)w * n_stride];
+            ue_wait_acc(L, c);
+            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
+            ue_epi_hidden<false, NCH>(L, c, tm, tx, cf, L.dl[5], mask, false, inv_s_h);
+            ue_operand_ready(L);
+        }
+        // ---- G1T: g = gh1 @ (W1 Wmix1^T) + gv @ Wmix^T ---------------------------------------
+        {
+            const float ca = inv_s_h * __ldg(scal + k * 8 + 5), cb = inv_s_gv * __ldg(scal + k * 8 + 6);
+            ue_wait_acc(L, c);
+            float a[8], b[8];
+            const UType& t5 = L.t[5];
+            const UType& t6 = L.t[6];
+            ue_acc8(tl + t5.dcol + UE_DQ * c.g, tl + t5.dcol + t5.nbh + UE_DQ * c.g, ca, L.dl[6], a);
+            ue_acc8(tl + t6.dcol + UE_DQ * c.g, tl + t6.dcol + t6.nbh + UE_DQ * c.g, cb, L.dl[7], b);
+#pragma unroll
+            for (int i = 0; i < UE_DQ; ++i) gs[i] = a[i] + b[i];
+        }
+    }
+    // the accumulators have been read: the next evaluation's first operand_ready releases the issuer
+    return lq;
+}
+
+// ---- kernel prologue / epilogue shared by the kernels --------------------------------------------
+struct UEnv { uint32_t rank, tmem; int warp, lane; };
+
+__device__ __forceinline__ UEnv ue_setup(const ULayout& L) {
+    UEnv e;
+    e.rank = umma::cluster_ctarank();
+    e.warp = threadIdx.x >> 5; e.lane = threadIdx.x & 31;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(ue_smem + L.s_bar + (2 * UE_NSTAGE + 2) * 8);
+    // operand buffers start from zero: pad rows, bias chunks and lo planes of the "ones" columns
+    for (int i = threadIdx.x; i < L.s_ring / 16; i += UE_THREADS) reinterpret_cast<uint4*>(ue_smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        const UBars B = ue_bars(L);
+        for (int s = 0; s < UE_NSTAGE; ++s) { umma::mbar_init(B.full + s, e.rank == 0 ? 2 : 1); umma::mbar_init(B.empty + s, 1); }
+        umma::mbar_init(B.dfull, 1);
+        umma::mbar_init(B.aready, 16);
+        umma::mbar_fence_init();
+    }
+    if (e.warp == 8) umma::tmem_alloc<2>(slot, 512);
+    umma::fence_proxy_async();
+    umma::tc_fence_before();
+    umma::cluster_sync_all();
+    umma::tc_fence_after();
+    e.tmem = *slot;
+    return e;
+}
+__device__ __forceinline__ void ue_teardown(const UEnv& e) {
+    umma::tc_fence_before();
+    umma::cluster_sync_all();
+    if (e.warp == 8) umma::tmem_free<2>(e.tmem, 512);
+}
+__device__ __forceinline__ UCw ue_cw(const UEnv& e) {
+    UCw c;
+    const int q4 = e.warp & 3;
+    const int l = 32 * q4 + e.lane;
+    c.r = l & 63; c.h = l >> 6; c.g = e.warp >> 2; c.q = 2 * c.g + c.h;
+    c.tl = (uint32_t)(32 * q4) << 16;
+    c.gi = 0; c.xb = 0; c.tmem = e.tmem; c.rank = e.rank;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3/K4 on the row-tile engine: x[n,d] -> log_q[n] (+ d log q / dx)
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD, int NCH>
+__global__ void __launch_bounds__(UE_THREADS, 1)
+k_flow_logprob_u(ULayout L, const uint8_t* __restrict__ blob, const float* __restrict__ x, float* __restrict__ log_q,
+                 float* __restrict__ grad, uint32_t* mscratch, long long n) {
+    const UEnv e = ue_setup(L);
+    const long long row0 = (long long)(blockIdx.x >> 1) * 128 + (long long)e.rank * UE_ROWS;
+    const long long n_stride = (long long)gridDim.x * UE_ROWS;
+    if (e.warp < 8) {
+        UCw c = ue_cw(e);
+        const long long grow = row0 + c.r;
+        const bool live = grow < n;
+        float zc[UE_DQ], gs[UE_DQ];
+        if (live) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + grow * L.d + UE_DQ * c.q));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(x + grow * L.d + UE_DQ * c.q + 4));
+            zc[0] = a.x; zc[1] = a.y; zc[2] = a.z; zc[3] = a.w; zc[4] = b.x; zc[5] = b.y; zc[6] = b.z; zc[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < UE_DQ; ++i) zc[i] = 0.f;
+        }
+        UE_T0();
+        const float lq = ue_flow_eval<GRAD, NCH>(L, c, reinterpret_cast<const float*>(blob), mscratch, n_stride,
+                                            (long long)blockIdx.x * UE_ROWS + c.r, zc, gs);
+        UE_ACC(7, blockIdx.x == 0 && threadIdx.x == 0);
+        if (live) {
+            if (c.q == 0) log_q[grow] = lq;
+            if (GRAD) {
+                float4* gp = reinterpret_cast<float4*>(grad + grow * L.d + UE_DQ * c.q);
+                gp[0] = make_float4(gs[0], gs[1], gs[2], gs[3]);
+                gp[1] = make_float4(gs[4], gs[5], gs[6], gs[7]);
+            }
+        }
+    } else if (e.warp == 8) {
+        if (e.rank == 0) ue_mma(L, e.tmem, 1, GRAD); else ue_relay(L, 1, GRAD);
+    } else {
+        ue_producer(L, blob, e.rank, 1, GRAD);
+    }
+    ue_teardown(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused HMC outer step on the row-tile engine (hmc.py:129-160; same contract as k_hmc_step)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ue_load8(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ue_store8(float* __restrict__ p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// (grid_reduce_last and hmc_finish: tile_kernels.cuh, included first by fab_b200.cu)
+template <int NCH>
+__global__ void __launch_bounds__(UE_THREADS, 1)
+k_hmc_step_u(ULayout L, const uint8_t* __restrict__ blob, fab_target_desc tgt, fab_hmc_state st, fab_hmc_args a,
+             fab_point cur, fab_point prop_in, fab_point prop_out, float* __restrict__ log_w,
+             const float* __restrict__ mom_noise, const float* __restrict__ exp_noise,
+             const int* __restrict__ n_active, float* __restrict__ stats, float* ws, uint32_t* mscratch, long long n) {
+    const UEnv e = ue_setup(L);
+    __shared__ float s_rowc[UE_ROWS], s_rowd[UE_ROWS], s_blk[8];
+    const long long n_act = n_active ? (long long)(*n_active) : n;
+    const long long pair0 = (long long)(blockIdx.x >> 1) * 128;
+    const long long row0 = pair0 + (long long)e.rank * UE_ROWS;
+    const bool pair_live = pair0 < n_act;
+    int np = (int)min((long long)UE_ROWS, n_act - row0);
+    if (np < 0) np = 0;
+    if (threadIdx.x < 8) s_blk[threadIdx.x] = 0.f;
+    if (pair_live) {
+        if (e.warp < 8) {
+            UCw c = ue_cw(e);
+            const long long grow = row0 + c.r;
+            const bool live = c.r < np;
+            const int d = L.d, c0 = UE_DQ * c.q;
+            float px[8], pgq[8], pgp[8], mom[8], mass[8];
+            float clq = 0.f, clp = 0.f, plq = 0.f, plp = 0.f;
+            ue_load8(st.d_mass + c0, mass);
+            if (live) {
+                const fab_point& src = prop_in.d_x ? prop_in : cur;
+                ue_load8(src.d_x + grow * d + c0, px);
+                ue_load8(src.d_grad_log_q + grow * d + c0, pgq);
+                ue_load8(src.d_grad_log_p + grow * d + c0, pgp);
+                plq = src.d_log_q[grow]; plp = src.d_log_p[grow];
+                clq = cur.d_log_q[grow]; clp = cur.d_log_p[grow];
+                ue_load8(mom_noise + grow * d + c0, mom);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { px[i] = 0.f; pgq[i] = 0.f; pgp[i] = 0.f; mom[i] = 0.f; }
+            }
+            const float eps = __fadd_rn(st.d_epsilons[(size_t)(a.i - 1) * st.n_outer + a.outer], st.d_common_epsilon[0]);
+            // momentum p0 = randn * mass (hmc.py:134), kinetic energy sum(p^2/m)/2
+            float kpart = 0.f, zero = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                mom[i] = __fmul_rn(mom[i], mass[i]);
+                kpart += __fdiv_rn(__fmul_rn(mom[i], mom[i]), mass[i]);
+            }
+            ue_row_sum2(L, c, kpart, zero);
+            const float ke0 = 0.5f * kpart;
+            // leapfrog (hmc.py:138-147)
+            for (int l = 0; l < a.L; ++l) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float gu = grad_u_of(a.g, pgq[i], pgp[i], a.max_grad);
+                    mom[i] = __fsub_rn(mom[i], __fmul_rn(__fmul_rn(eps, gu), 0.5f));
+                    px[i] = __fadd_rn(px[i], __fmul_rn(__fdiv_rn(eps, mass[i]), mom[i]));
+                }
+                float zc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zc[i] = px[i];
+                plq = ue_flow_eval<true, NCH>(L, c, reinterpret_cast<const float*>(blob), mscratch,
+                                         (long long)gridDim.x * UE_ROWS, (long long)blockIdx.x * UE_ROWS + c.r, zc, pgq);
+                // many-well target: value and gradient of the thread's columns (pairs stay in one thread)
+                float epart = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float ej, gj;
+                    manywell_elem(tgt, px[i], c0 + i, ej, gj);
+                    epart += ej;
+                    pgp[i] = gj;
+                }
+                zero = 0.f;
+                ue_row_sum2(L, c, epart, zero);
+                plp = -epart - tgt.log_norm;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float gu = grad_u_of(a.g, pgq[i], pgp[i], a.max_grad);
+                    mom[i] = __fsub_rn(mom[i], __fmul_rn(__fmul_rn(eps, gu), 0.5f));
+                }
+            }
+            // Metropolis accept (hmc.py:105-124) and distance moved (hmc.py:173-183)
+            float cx[8];
+            if (live) ue_load8(cur.d_x + grow * d + c0, cx);
+            float kp = 0.f, dd = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                kp += __fdiv_rn(__fmul_rn(mom[i], mom[i]), mass[i]);
+                const float df = live ? cx[i] - px[i] : 0.f;
+                dd += df * df;
+            }
+            ue_row_sum2(L, c, kp, dd);
+            bool acc = false;
+            if (live) {
+                const float lj_cur = __fsub_rn(gamma_of(a.g, clq, clp), ke0);
+                const float lj_prop = __fsub_rn(gamma_of(a.g, plq, plp), 0.5f * kp);
+                float log_a = __fsub_rn(lj_prop, lj_cur);
+                const bool ok = fab_isfinite(log_a);
+                if (!ok) log_a = -CUDART_INF_F;
+                acc = ok && (log_a > -__ldg(exp_noise + grow));
+                if (c.q == 0) { s_rowc[c.r] = expf(fminf(log_a, 0.f)); s_rowd[c.r] = acc ? 0.f : sqrtf(dd); }
+            } else if (c.q == 0) { s_rowc[c.r] = 0.f; s_rowd[c.r] = 0.f; }
+            if (live) {
+                if (acc) {       // cur[accept] = prop[accept]  (hmc.py:154)
+                    ue_store8(cur.d_x + grow * d + c0, px);
+                    ue_store8(cur.d_grad_log_q + grow * d + c0, pgq);
+                    ue_store8(cur.d_grad_log_p + grow * d + c0, pgp);
+                    clq = plq; clp = plp;
+                }
+                if (c.q == 0) {
+                    if (acc) { cur.d_log_q[grow] = clq; cur.d_log_p[grow] = clp; }
+                    if (a.update_log_w) {   // ais.py:93-100
+                        const float inc = __fsub_rn(gamma_of(a.g_next, clq, clp), gamma_of(a.g_w, clq, clp));
+                        log_w[grow] = __fadd_rn(log_w[grow], inc);
+                    }
+                }
+                if (prop_out.d_x) {
+                    ue_store8(prop_out.d_x + grow * d + c0, px);
+                    ue_store8(prop_out.d_grad_log_q + grow * d + c0, pgq);
+                    ue_store8(prop_out.d_grad_log_p + grow * d + c0, pgp);
+                    if (c.q == 0) { prop_out.d_log_q[grow] = plq; prop_out.d_log_p[grow] = plp; }
+                }
+            }
+        } else if (e.warp == 8) {
+            if (e.rank == 0) ue_mma(L, e.tmem, a.L, true); else ue_relay(L, a.L, true);
+        } else {
+            ue_producer(L, blob, e.rank, a.L, true);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && pair_live) {
+        float s = 0.f, dsum = 0.f;
+        for (int p = 0; p < np; ++p) { s += s_rowc[p]; dsum += s_rowd[p]; }
+        s_blk[0] = s; s_blk[1] = dsum;
+    }
+    __syncthreads();
+    if (grid_reduce_last<2>(s_blk, ws, s_blk + 4)) {
+        if (threadIdx.x == 0) {
+            stats[0] = s_blk[4]; stats[1] = (float)n_act; stats[2] = s_blk[5]; stats[3] = 0.f;
+            if (!a.defer_stats) hmc_finish(st, a, s_blk[4], (float)n_act, s_blk[5]);
+        }
+    }
+    ue_teardown(e);
+}

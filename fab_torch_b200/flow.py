@@ -152,6 +152,9 @@ class B200RealNVP(TrainableDistribution):
         self._desc = _lib.FlowDesc()
         self._blob = None
         self._blob_key = None
+        self._ublob = None              # row-tile engine weight images (f16 hi/lo planes)
+        self._ublob_key = None
+        self._uws = None
         self._eps_override = None       # test hook: next sample uses this base noise
         # filled lazily: needs the .so
         self._desc_ready = False
@@ -256,6 +259,84 @@ class B200RealNVP(TrainableDistribution):
         assert blob.numel() == d.total_floats
         return blob
 
+    # ---- row-tile engine (tcgen05): weight images and engine choice ------------------------------
+    def rowtile_supported(self) -> bool:
+        return bool(_lib.lib().fab_umma_supported(self.desc()))
+
+    def use_rowtile(self, n: int) -> bool:
+        mode = _lib.engine_choice()
+        if mode == "warp":
+            return False
+        if not self.rowtile_supported():
+            if mode == "rowtile":
+                raise RuntimeError("FAB_ENGINE=rowtile: this flow shape is not covered by the row-tile "
+                                   "engine (needs dim 32, width 64..320 in steps of 64, <= 10 layers)")
+            return False
+        return mode == "rowtile" or n >= _lib.rowtile_min_n()
+
+    def umma_blob(self) -> torch.Tensor:
+        """Weight images of the row-tile engine (include/fab_b200.h), rebuilt on the device when a
+        parameter changed: merged fp32 matrices in a plain buffer -> fab_umma_pack_f32."""
+        key = self._param_key()
+        if self._ublob is None or key != self._ublob_key:
+            with torch.no_grad():
+                plain = self._plain_umma()
+                L = _lib.lib()
+                nbytes = int(L.fab_umma_blob_bytes(self.desc()))
+                _lib.check(nbytes, "fab_umma_blob_bytes")
+                if self._ublob is None or self._ublob.numel() != nbytes or self._ublob.device != plain.device:
+                    self._ublob = torch.zeros(nbytes, dtype=torch.uint8, device=plain.device)
+                rc = L.fab_umma_pack_f32(self.desc(), _lib.ptr(plain), _lib.ptr(self._ublob),
+                                         _lib.stream_ptr(plain.device))
+                _lib.check(rc, "fab_umma_pack_f32")
+            self._ublob_key = key
+        return self._ublob
+
+    def _plain_umma(self) -> torch.Tensor:
+        """[loc | log_scale | per layer: the seven operand matrices M[k][n] (+ bias rows), sum(log_S)]
+        in the float layout `fab_umma_plain_layout` reports.  Merged products in float64."""
+        import ctypes as C
+        d = self.desc()
+        offs = (C.c_int64 * 32)()
+        _lib.check(_lib.lib().fab_umma_plain_layout(d, offs), "fab_umma_plain_layout")
+        total, off_layers, per_layer, logs_off = (int(offs[i]) for i in range(4))
+        K, dd, d1, W = self.n_flow_layers, d.dim, d.d1, d.width
+        blocks = [self._nf_model.flows[2 * k] for k in range(K)]
+        W1 = torch.stack([b.linears[0].weight for b in blocks])     # [K, W, d1]
+        b1 = torch.stack([b.linears[0].bias for b in blocks])
+        W2 = torch.stack([b.linears[1].weight for b in blocks])     # [K, W, W]
+        b2 = torch.stack([b.linears[1].bias for b in blocks])
+        W3 = torch.stack([b.linears[2].weight for b in blocks])     # [K, 2*d2, W]
+        b3 = torch.stack([b.linears[2].bias for b in blocks])
+        dev = W1.device
+        perm = torch.cat([torch.arange(0, 2 * d.d2, 2), torch.arange(1, 2 * d.d2, 2)]).to(dev)
+        W3, b3 = W3[:, perm, :], b3[:, perm]
+        Wm, _, logs = self._mixing()
+        t = lambda M: M.transpose(1, 2)
+        mw1 = torch.cat([Wm, (Wm[:, :, :d1].double() @ t(W1).double()).float()], dim=2)   # [K, d, d+W]
+        b1e = torch.cat([b1.new_zeros(K, dd), b1], dim=1)
+        w1mt = (W1.double() @ t(Wm[:, :, :d1]).double()).float()                         # [K, W, d]
+        mats = [(mw1, b1e), (t(W2), b2), (t(W3), b3), (W3, None), (W2, None), (w1mt, None), (t(Wm), None)]
+        layer = W1.new_zeros(K, per_layer)
+        for i, (M, bias) in enumerate(mats):
+            mo, bo, kk, nn_ = int(offs[4 + 2 * i]), int(offs[5 + 2 * i]), int(offs[18 + 2 * i]), int(offs[19 + 2 * i])
+            assert tuple(M.shape[1:]) == (kk, nn_), (i, M.shape, kk, nn_)
+            layer[:, mo:mo + kk * nn_] = M.reshape(K, -1)
+            if bias is not None:
+                layer[:, bo:bo + nn_] = bias
+        layer[:, logs_off] = logs
+        plain = torch.cat([self._nf_model.q0.loc.reshape(-1), self._nf_model.q0.log_scale.reshape(-1),
+                           layer.reshape(-1)]).contiguous()
+        assert plain.numel() == total and off_layers == 2 * dd
+        return plain
+
+    def _umma_ws(self, n: int, dev) -> torch.Tensor:
+        nbytes = int(_lib.lib().fab_umma_workspace_bytes(self.desc(), n))
+        _lib.check(nbytes, "fab_umma_workspace_bytes")
+        if self._uws is None or self._uws.numel() < nbytes or self._uws.device != dev:
+            self._uws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        return self._uws
+
     # ---- Distribution surface ----------------------------------------------------------------
     @property
     def event_shape(self) -> Tuple[int, ...]:
@@ -294,6 +375,12 @@ class B200RealNVP(TrainableDistribution):
         n = x.shape[0]
         log_q = torch.empty(n, dtype=torch.float32, device=x.device)
         grad = torch.empty_like(x) if with_grad else None
+        if n > 0 and self.use_rowtile(n):
+            rc = _lib.lib().fab_flow_logprob_grad_umma_f32(
+                self.desc(), _lib.ptr(self.umma_blob()), _lib.ptr(x), _lib.ptr(log_q), _lib.ptr(grad),
+                _lib.ptr(self._umma_ws(n, x.device)), n, _lib.stream_ptr(x.device))
+            _lib.check(rc, "fab_flow_logprob_grad_umma_f32")
+            return log_q, grad
         rc = _lib.lib().fab_flow_logprob_grad_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(x),
                                                   _lib.ptr(log_q), _lib.ptr(grad), n,
                                                   _lib.stream_ptr(x.device))

@@ -311,11 +311,18 @@ class HamiltonianMonteCarlo(TransitionOperator):
         else:
             mom = self.noise.momentum(i, self.n_outer, n, d, dev)
             exp = self.noise.exponential(i, self.n_outer, n, dev)
-        ws = self._workspace(int(L.fab_hmc_workspace_bytes(flow.desc(), n)), dev)
+        tdesc = target.target_desc(dev)
+        rowtile = tdesc.kind == _lib.FAB_TARGET_MANYWELL and flow.use_rowtile(n)
+        if rowtile:
+            ws = self._workspace(int(L.fab_umma_workspace_bytes(flow.desc(), n)), dev)
+            blob = flow.umma_blob()
+            step = L.fab_hmc_step_umma_f32
+        else:
+            ws = self._workspace(int(L.fab_hmc_workspace_bytes(flow.desc(), n)), dev)
+            blob = flow.blob()
+            step = L.fab_hmc_step_f32
         world = self._world()
         st = self._state()
-        blob = flow.blob()
-        tdesc = target.target_desc(dev)
         stream = _lib.stream_ptr(dev)
         null_pt = _lib.PointPtrs(None, None, None, None, None)
         prop_in = null_pt
@@ -325,13 +332,13 @@ class HamiltonianMonteCarlo(TransitionOperator):
                                 self.target_p_accept, self.max_grad, g,
                                 1 if (fuse_w and last) else 0, g_w, g_next, 1 if world > 1 else 0)
             prop_out = null_pt if last else _lib.point_ptrs(self._prop_point(point, no & 1))
-            rc = L.fab_hmc_step_f32(flow.desc(), _lib.ptr(blob), tdesc, st, args,
-                                    _lib.point_ptrs(point), prop_in, prop_out,
-                                    _lib.ptr(log_w) if log_w is not None else None,
-                                    _lib.ptr(mom[no]), _lib.ptr(exp[no]),
-                                    _lib.ptr(n_active) if n_active is not None else None,
-                                    _lib.ptr(self._stats), _lib.ptr(ws), n, stream)
-            _lib.check(rc, "fab_hmc_step_f32")
+            rc = step(flow.desc(), _lib.ptr(blob), tdesc, st, args,
+                      _lib.point_ptrs(point), prop_in, prop_out,
+                      _lib.ptr(log_w) if log_w is not None else None,
+                      _lib.ptr(mom[no]), _lib.ptr(exp[no]),
+                      _lib.ptr(n_active) if n_active is not None else None,
+                      _lib.ptr(self._stats), _lib.ptr(ws), n, stream)
+            _lib.check(rc, "fab_hmc_step_umma_f32" if rowtile else "fab_hmc_step_f32")
             if world > 1:
                 fdist.reduce_stats(self._stats[:4], self.process_group)
                 _lib.check(L.fab_hmc_finish_f32(st, args, _lib.ptr(self._stats), stream),

@@ -291,6 +291,52 @@ int fab_buffer_adjust_f32(float* d_buf_log_w, float* d_buf_log_q, const int64_t*
                           const float* d_log_w_adjustment, const float* d_log_q, int64_t m,
                           void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Row-tile engine: the same flow evaluation (fab/wrappers/normflows.py:20-24 log_prob, its input
+ * gradient as used by fab/sampling_methods/base.py:50-56) and the same fused HMC outer step
+ * (transition_operators/hmc.py:129-160) on the 5th-generation tensor cores: tcgen05.mma with
+ * cta_group::2 (a CTA pair carries 128 particles), accumulators in tensor memory, weight stages
+ * streamed into shared memory by the TMA engine (cp.async.bulk).  Covers dim = 32 with
+ * d1 = d2 = 16, width in {64,128,...,320}, <= 10 coupling layers (BASELINE configs 2 and 3) and the
+ * many-well target; everything else stays on the warp-level engine above.
+ *
+ * Weight images ("ublob", bytes): [scalar block | layer 0 | layer 1 | ...].  Scalar block (fp32):
+ * loc[32], log_scale[32], then per layer 8 floats: for the seven operand types t = 0..6 the
+ * un-scaling factor (1/s_t)(1 + 1.67e-8 KS_t) and sum(log_S).  A layer block holds, for each
+ * operand type and each CTA rank of the pair, the f16 image the tensor core reads:
+ *     image[k-chunk c][row][8 halves]       (one "core matrix" = 8 rows x 16 bytes, no swizzle)
+ * k-chunk c = logical k 8c..8c+7 (k == K: the bias row; beyond: zero).  Rows of a rank:
+ *   wide types  (0: z->[h1pre|v], 1: h1->h2pre, 3: gparam->gh2, 4: gh2->gh1): for column block
+ *     g = 0,1: N/4 rows "hi" then N/4 rows "lo" of the output columns owned by thread group
+ *     q = 2g + rank, i.e. columns [q N/4, (q+1) N/4)   (type 0: W/4 hidden columns, then 8 v columns);
+ *   narrow types (2: h2->[shift|scale], 5: gh1->g, 6: gv->g): N/2 rows "hi" then N/2 rows "lo" of
+ *     columns 8 rank + (0..7), then 16 + 8 rank + (0..7).
+ * value = hi + lo = M[k][n] * s_t, s_t = the power of two that puts max|M| in [2^13, 2^14).
+ * The images are produced on the device by fab_umma_pack_f32 from a plain fp32 buffer:
+ * [loc | log_scale | per layer: M_0 [K_0][N_0], bias_0 [N_0], M_1, bias_1, M_2, bias_2, M_3 .. M_6,
+ * sum(log_S), 3 pad]; fab_umma_plain_layout reports the offsets.
+ * ------------------------------------------------------------------------------------- */
+int     fab_umma_supported(const fab_flow_desc* flow);       /* 1 if this flow shape is covered */
+int64_t fab_umma_blob_bytes(const fab_flow_desc* flow);
+/* offs[32]: [0] total floats of the plain buffer, [1] offset of layer 0, [2] floats per layer,
+ * [3] offset of sum(log_S) in a layer, [4+2t],[5+2t] matrix / bias offset of type t (-1: no bias),
+ * [18+2t],[19+2t] its (K, N). */
+int     fab_umma_plain_layout(const fab_flow_desc* flow, int64_t* offs);
+int     fab_umma_pack_f32(const fab_flow_desc* flow, const float* d_plain, void* d_ublob, void* stream);
+/* caller-owned scratch: cross-CTA reduction slots + ReLU masks of the input-gradient sweep
+ * (960 bytes per particle, L2 resident).  Must be zero on first use. */
+int64_t fab_umma_workspace_bytes(const fab_flow_desc* flow, int64_t n);
+/* = fab_flow_logprob_grad_f32 (d_grad may be NULL); d_x / d_grad 16-byte aligned. */
+int fab_flow_logprob_grad_umma_f32(const fab_flow_desc* flow, const void* d_ublob, const float* d_x,
+                                   float* d_log_q, float* d_grad, void* d_workspace, int64_t n,
+                                   void* stream);
+/* = fab_hmc_step_f32 (same arguments and semantics); many-well target only. */
+int fab_hmc_step_umma_f32(const fab_flow_desc* flow, const void* d_ublob, const fab_target_desc* target,
+                          fab_hmc_state st, fab_hmc_args args, fab_point cur, fab_point prop_in,
+                          fab_point prop_out, float* d_log_w, const float* d_mom_noise,
+                          const float* d_exp_noise, const int32_t* d_n_active, float* d_stats,
+                          void* d_workspace, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ struct Params {
     float* dump;               // per CTA [128][ncols]
     uint32_t ncols;
     unsigned long long* cycles;
+    uint32_t ld16_off8;        // 1: dump columns [8, ncols-8) with x16 loads whose column is 8 mod 16
 };
 
 extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -87,6 +88,13 @@ __global__ void __launch_bounds__(128, 1) k_run(Params p) {
         umma::tmem_ld_wait();
         for (int j = 0; j < 8; ++j) out[(size_t)(32 * warp + lane) * p.ncols + c + j] = __uint_as_float(v[j]);
     }
+    if (p.ld16_off8)
+        for (uint32_t c = 8; c + 16 <= p.ncols; c += 16) {
+            uint32_t v[16];
+            umma::tmem_ld16(tbase + ((uint32_t)(32 * warp) << 16) + c, v);
+            umma::tmem_ld_wait();
+            for (int j = 0; j < 16; ++j) out[(size_t)(32 * warp + lane) * p.ncols + c + j] = __uint_as_float(v[j]);
+        }
     umma::tc_fence_before();
     if (CG == 2) umma::cluster_sync_all(); else __syncthreads();
     if (warp == 0) umma::tmem_free<CG>(tbase, 512);
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(128, 1) k_run(Params p) {
 // tight issue loop: descriptors advance by a constant, 8 MMAs per unrolled iteration
 template <int CG, bool KIND16>
 __global__ void __launch_bounds__(128, 1) k_rate(uint32_t idesc, uint32_t lbo_a, uint32_t lbo_b, uint32_t iters,
-                                                 unsigned long long* cycles, uint32_t nacc_mask, uint32_t acc_stride) {
+                                                 unsigned long long* cycles, uint32_t nacc_mask, uint32_t acc_stride, uint32_t uniform) {
     __shared__ __align__(8) uint64_t bar_done;
     __shared__ uint32_t tmem_slot;
     const uint32_t rank = CG == 2 ? umma::cluster_ctarank() : 0;
@@ -108,7 +116,22 @@ __global__ void __launch_bounds__(128, 1) k_rate(uint32_t idesc, uint32_t lbo_a,
     if (CG == 2) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
     const uint32_t tbase = tmem_slot;
-    if (rank == 0 && threadIdx.x == 0) {
+    if (uniform && rank == 0 && warp == 0) {
+        // whole warp in the loop, one elected lane issues: operands stay warp-uniform
+        const uint32_t sbase = umma::smem_u32(smem_raw);
+        const uint64_t a0 = umma::smem_desc(sbase, lbo_a, 128), b0 = umma::smem_desc(sbase + 16384, lbo_b, 128);
+        const long long t0 = clock64();
+        for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (umma::elect_one())
+                    umma::mma_ss<CG, KIND16>(tbase + (j & nacc_mask) * acc_stride, a0 + (uint64_t)(j & 3) * 2, b0 + (uint64_t)(j & 3) * 2, idesc, true);
+        }
+        if (umma::elect_one()) umma::mma_commit<CG>(&bar_done, 3);
+        __syncwarp();
+        umma::mbar_wait(&bar_done, 0);
+        if (threadIdx.x == 0) *cycles = (unsigned long long)(clock64() - t0);
+    } else if (!uniform && rank == 0 && threadIdx.x == 0) {
         const uint32_t sbase = umma::smem_u32(smem_raw);
         const uint64_t a0 = umma::smem_desc(sbase, lbo_a, 128), b0 = umma::smem_desc(sbase + 16384, lbo_b, 128);
         const long long t0 = clock64();
@@ -128,7 +151,7 @@ __global__ void __launch_bounds__(128, 1) k_rate(uint32_t idesc, uint32_t lbo_a,
     if (warp == 0) umma::tmem_free<CG>(tbase, 512);
 }
 
-static void test_rate_tight(int CG, bool kind16, int M, int N, int nacc = 2) {
+static void test_rate_tight(int CG, bool kind16, int M, int N, int nacc = 2, uint32_t uniform = 0) {
     unsigned long long* d_cyc; CK(cudaMalloc(&d_cyc, 8));
     void* fn = CG == 1 ? (kind16 ? (void*)k_rate<1, true> : (void*)k_rate<1, false>)
                        : (kind16 ? (void*)k_rate<2, true> : (void*)k_rate<2, false>);
@@ -140,13 +163,13 @@ static void test_rate_tight(int CG, bool kind16, int M, int N, int nacc = 2) {
     cfg.attrs = at; cfg.numAttrs = 1;
     uint32_t idesc = umma::instr_desc(kind16 ? umma::FMT_F16 : umma::FMT_TF32, M, N), la = 64, lb = 64, iters = 256;
     uint32_t nmask = nacc - 1, astride = 512 / nacc;
-    void* args[] = {&idesc, &la, &lb, &iters, &d_cyc, &nmask, &astride};
+    void* args[] = {&idesc, &la, &lb, &iters, &d_cyc, &nmask, &astride, &uniform};
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("tight CG=%d M=%d N=%d : %s\n", CG, M, N, cudaGetErrorString(e)); exit(1); }
     unsigned long long cyc; CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
     const double per = (double)cyc / (iters * 8);
-    printf("tight nacc=%d CG=%d %s M=%3d N=%3d : %6.1f cycles/MMA -> %6.0f FLOP/cycle/SM (floor %d)\n", nacc, CG, kind16 ? "f16 " : "tf32", M, N, per,
+    printf("tight%s nacc=%d CG=%d %s M=%3d N=%3d : %6.1f cycles/MMA -> %6.0f FLOP/cycle/SM (floor %d)\n", uniform ? "(uniform)" : "", nacc, CG, kind16 ? "f16 " : "tf32", M, N, per,
            2.0 * M * N * (kind16 ? 16 : 8) / per / CG, M * N / (256 * CG));
     cudaFree(d_cyc);
 }
@@ -160,7 +183,7 @@ struct Run {
     int rowsA = 128, rowsB = 64;                            // rows held per CTA
     std::vector<uint8_t> image[2];
     std::vector<Op> ops;
-    int ncols = 64, reps = 1;
+    int ncols = 64, reps = 1, ld16_off8 = 0;
     std::vector<float> dump;                                // [CG][128][ncols]
     unsigned long long cycles = 0;
 };
@@ -175,7 +198,7 @@ static void launch(Run& r) {
     CK(cudaMemset(d_dump, 0xff, sizeof(float) * 128 * r.ncols * r.CG));
     Params p{d_img, (uint32_t)ib, d_ops, (uint32_t)r.ops.size(), (uint32_t)r.reps,
              umma::instr_desc(r.kind16 ? umma::FMT_F16 : umma::FMT_TF32, r.M, r.N), (uint32_t)r.rowsA * 16,
-             (uint32_t)r.rowsB * 16, d_dump, (uint32_t)r.ncols, d_cyc};
+             (uint32_t)r.rowsB * 16, d_dump, (uint32_t)r.ncols, d_cyc, (uint32_t)r.ld16_off8};
     void* fn = r.CG == 1 ? (r.kind16 ? (void*)k_run<1, true> : (void*)k_run<1, false>)
                          : (r.kind16 ? (void*)k_run<2, true> : (void*)k_run<2, false>);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((ib + 1023) / 1024 * 1024)));
@@ -202,8 +225,8 @@ static void put32(std::vector<uint8_t>& img, size_t base, int R, int r, int k, f
 }
 
 // ---- test 1: layout / descriptor validation with small integers (exact) ----------------------------
-static int test_layout(int CG, bool kind16, int N, int K) {
-    Run r; r.CG = CG; r.kind16 = kind16; r.M = 128; r.N = N;
+static int test_layout(int CG, bool kind16, int N, int K, int ld16_off8 = 0) {
+    Run r; r.ld16_off8 = ld16_off8; r.CG = CG; r.kind16 = kind16; r.M = 128; r.N = N;
     r.rowsA = 128 / CG; r.rowsB = N / CG; r.ncols = N / CG; r.reps = 1;
     const int es = kind16 ? 2 : 4, kstep = kind16 ? 16 : 8;
     const size_t offA = 0, szA = (size_t)r.rowsA * K * es, offB = szA, szB = (size_t)r.rowsB * K * es;
@@ -394,6 +417,14 @@ int main(int argc, char** argv) {
     if (on("nacc")) {
         for (int na : {1, 2, 4, 8}) { test_rate_tight(2, true, 128, 32, na); test_rate_tight(2, true, 128, 64, na); test_rate_tight(1, true, 128, 32, na); }
         test_rate_tight(2, true, 128, 160, 1); test_rate_tight(2, true, 128, 160, 2); test_rate_tight(2, true, 128, 256, 1);
+    }
+    if (on("ldalign")) {       // x16 tensor-memory loads at a column that is 8 mod 16: same data?
+        test_layout(1, true, 160, 32, 1);
+        test_layout(2, true, 256, 32, 1);
+    }
+    if (on("uniform")) {
+        for (int n : {32, 64, 96, 128, 160, 192, 256}) test_rate_tight(2, true, 128, n, 2, 1);
+        for (int n : {16, 32, 64, 128, 256}) test_rate_tight(1, true, 128, n, 2, 1);
     }
     if (on("tightodd")) { test_rate_tight(2, true, 128, 176); test_rate_tight(2, true, 128, 48); test_rate_tight(2, true, 128, 16); }
     if (on("round")) {

@@ -87,14 +87,18 @@ def test_state_dict_roundtrip_and_repack():
     assert torch.equal(a, c)
 
 
-def test_results_do_not_depend_on_the_batch_they_are_evaluated_in():
-    """A particle's log q / gradient / sample is bit-identical whether it is evaluated alone, in a
+def test_results_do_not_depend_on_the_batch_they_are_evaluated_in(monkeypatch):
+    """(Warp-level engine; the row-tile engine's twin is tests/test_gpu_rowtile.py.  FAB_ENGINE=auto
+    switches engines with the batch size, and the two engines round differently, so the property
+    holds per engine.)
+    A particle's log q / gradient / sample is bit-identical whether it is evaluated alone, in a
     batch that maps to the 8-slot tile layout or in one that maps to the 16-slot layout (different
     particles per CTA): MMA rows are independent and every per-particle reduction runs in a
     canonical order.  This is what makes rank-sharded runs equal single-device runs bit for bit."""
     def same(a, b):                      # bitwise equality that treats NaN == NaN
         return torch.equal(torch.nan_to_num(a, nan=12345.0), torch.nan_to_num(b, nan=12345.0))
 
+    monkeypatch.setenv("FAB_ENGINE", "warp")
     _, _, fp = make_flows(32, 10, 10, last_std=0.05)
     g = torch.Generator().manual_seed(11)
     x = (torch.randn(2048, 32, generator=g) * 1.5).cuda()
