@@ -10,9 +10,17 @@ HMC L=5 / n_outer=1 (tuner on), 2048 particles per GPU (weak scaling: N GPUs car
 particles sharded over ranks; the only exchanges are the scalar ESS all-gather and the tuner's
 all-reduce).  Prints ONE JSON line on rank 0 (contract in the task statement); see DESIGN.md §6.
 
-`--impl reference` times the CPU port of the reference path (oracle/, pinned bit-for-bit against
-the reference in the build container; the reference itself is Python and cannot travel) on the
-host cores.
+Initial HMC step size eps0 = 0.1 (the reference's own many_well.yaml value is 1.0): with eps0 = 1
+and a randomly initialised flow every proposal is rejected for the first ~10 calls and, once the
+tuner has found an accepting step size, chains escape along directions where q decays faster than
+p^2 and log Z reaches 1e37 (profiles/r02_workload_sanity.log; the reference does the same).  With
+eps0 = 0.1 the chain accepts from the first call and log Z stays finite over the whole run; the
+work per step (flow passes, launches) is identical.
+
+`--impl reference` times the UNMODIFIED reference (AnnealedImportanceSampler, HamiltonianMonteCarlo,
+ManyWellEnergy from baseline/_ref, installed by __graft_entry__.build()) on the host cores; the
+flow object handed to it is oracle.realnvp.OracleRealNVP, because the reference's flow lives in the
+third-party package `normflows`, which is not installable here (flow parity: unpinned).
 """
 import argparse
 import json
@@ -29,11 +37,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CFG = dict(dim=32, n_layers=10, nodes_per_dim=10, M=16, L=5, n_outer=1, epsilon=1.0,
+CFG = dict(dim=32, n_layers=10, nodes_per_dim=10, M=16, L=5, n_outer=1, epsilon=0.1,
            batch_per_gpu=2048, alpha=2.0, p_target=False)
 METRIC = "ais_particles_per_sec"
 UNIT = "particles/s"
 WORKLOAD = "manywell32_realnvp10x320_M16_hmcL5_b2048_per_gpu"
+
+
+def config_block(cfg, world):
+    """Identical in both arms (the driver compares them)."""
+    return dict(workload=WORKLOAD, global_batch=cfg["batch_per_gpu"] * world, eps0=cfg["epsilon"],
+                tuner="on", l2_flush_between_steps=True, flow_parity="unpinned",
+                **{k: cfg[k] for k in ("dim", "n_layers", "M", "L", "n_outer")})
 
 
 def flops_per_particle_flow_pass(dim, K, W):
@@ -86,24 +101,60 @@ def build_cpu_port(cfg, batch):
     return ais
 
 
-def time_cpu_port(cfg, batch, steps, warmup):
+def build_cpu_reference(cfg, dtype=torch.float32):
+    """The reference's own classes (baseline/_ref, unmodified) around the restated flow.  Returns
+    (sampler, kind): kind = "reference" or, if baseline/_ref is absent, "port" (oracle/sampler.py,
+    pinned bit-for-bit against the reference: tests/golden/pin_report.json)."""
+    from oracle.ref_loader import installed_reference_available, load_reference
+    if not installed_reference_available():
+        return build_cpu_port(cfg, cfg["batch_per_gpu"]), "port"
+    load_reference(installed=True)
+    from fab.sampling_methods import AnnealedImportanceSampler, HamiltonianMonteCarlo
+    from fab.target_distributions.many_well import ManyWellEnergy
+    from oracle.realnvp import OracleRealNVP, randomize_last_layers
+    torch.manual_seed(0)
+    flow = OracleRealNVP(cfg["dim"], cfg["n_layers"], cfg["nodes_per_dim"])
+    randomize_last_layers(flow, 0.01, seed=1)
+    target = ManyWellEnergy(cfg["dim"], a=-0.5, b=-6.0, use_gpu=False)
+    if dtype == torch.float64:
+        flow, target = flow.double(), target.double()
+    op = HamiltonianMonteCarlo(cfg["M"], cfg["dim"], flow.log_prob, target.log_prob, alpha=cfg["alpha"],
+                               p_target=cfg["p_target"], epsilon=cfg["epsilon"], n_outer=cfg["n_outer"],
+                               L=cfg["L"])
+    if dtype == torch.float64:
+        op = op.double()
+    ais = AnnealedImportanceSampler(flow, target.log_prob, op, p_target=cfg["p_target"],
+                                    alpha=cfg["alpha"], n_intermediate_distributions=cfg["M"])
+    return ais, "reference"
+
+
+def time_cpu(cfg, batch, steps, warmup, dtype=torch.float32):
+    """Wall-clock of full `sample_and_log_weights(batch)` calls of the CPU arm on all host threads."""
     torch.set_num_threads(os.cpu_count() or 1)
-    ais = build_cpu_port(cfg, batch)
-    torch.manual_seed(1234)
-    for _ in range(warmup):
-        ais.sample_and_log_weights(batch)
-    ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        ais.sample_and_log_weights(batch)
-        ts.append(time.perf_counter() - t0)
-    return ts, ais.get_logging_info()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)          # the reference follows the default dtype (many_well.yaml:41)
+    try:
+        ais, kind = build_cpu_reference(cfg, dtype)
+        torch.manual_seed(1234)
+        for _ in range(warmup):
+            ais.sample_and_log_weights(batch)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            ais.sample_and_log_weights(batch)
+            ts.append(time.perf_counter() - t0)
+        return ts, ais.get_logging_info(), kind
+    finally:
+        torch.set_default_dtype(prev)
 
 
 def parity_leg(cfg, batch, device):
-    """log-Z / log-weight agreement of the CUDA chain with the CPU port on IDENTICAL noise: one
-    fresh-state `sample_and_log_weights(batch)` on each side (same weights, the CPU side records
-    every variate it draws and the CUDA side replays them).  BASELINE target: |dlogZ| <= 1e-3."""
+    """log-Z / log-weight agreement of the CUDA chain with the CPU arm on IDENTICAL noise: one
+    fresh-state `sample_and_log_weights(batch)` on each side (same weights; the CPU side -- the
+    oracle port, pinned bit-for-bit against the unmodified reference -- records every variate it
+    draws and the CUDA side replays them).  BASELINE target: |dlogZ| <= 1e-3.  The chain is chaotic
+    (80 leapfrog steps), so the per-particle errors are reported as a distribution plus the number
+    of rows above the 1e-5 bar; with an untrained flow a handful of particles carry log Z."""
     import copy
     import fab_torch_b200 as fb
     from oracle.noise import Float32RecordingNoise
@@ -139,6 +190,7 @@ def parity_leg(cfg, batch, device):
         div = dx > 1e-2 * (1 + pt_c.x.double().abs().max(dim=1).values)
         out.update(log_w_rel_err_median=float(e.median()), log_w_rel_err_p99=float(e.quantile(0.99)),
                    log_w_rel_err_max_same_branch=float(e[~div].max()) if (~div).any() else None,
+                   rows_above_1e5_bar=int((e[~div] > 1e-5).sum()), rows_compared=int((~div).sum()),
                    chains_on_other_accept_branch=int(div.sum()))
     return out
 
@@ -148,22 +200,21 @@ def run_reference_arm(args):
     if rank != 0:
         return
     batch = CFG["batch_per_gpu"]
-    ts, info = time_cpu_port(CFG, batch, args.steps, args.warmup)
+    ts, info, kind = time_cpu(CFG, batch, args.steps, args.warmup)
     total = float(np.sum(ts))
     value = batch * len(ts) / total
     cores = torch.get_num_threads()
-    sample = (f"each step = one full sample_and_log_weights({batch}) call of the workload "
-              f"(fp32, torch CPU, {cores} threads); particles/s is per-particle so the same figure "
-              f"holds for the {args.gpus}-GPU global batch")
+    sample = (f"each step = one full sample_and_log_weights({batch}) call of the workload through the "
+              f"{'unmodified reference classes (baseline/_ref)' if kind == 'reference' else 'oracle port'} "
+              f"(fp32, torch CPU, {cores} threads, ONE process); particles/s is per-particle, so the same "
+              f"figure is reported for the {args.gpus}-GPU global batch")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / len(ts), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=WORKLOAD, global_batch=batch * args.gpus, **{
-                    k: CFG[k] for k in ("dim", "n_layers", "M", "L", "n_outer")}),
-                impl="reference",
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                config=config_block(CFG, args.gpus), impl="reference",
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0, log_Z=info["log_Z"])
+                gpu_launches=0, log_Z_last_timed_call=info["log_Z"], ess_ais_last_timed_call=info["ess_ais"])
     print(json.dumps(line), flush=True)
 
 
@@ -315,14 +366,32 @@ def run_gpu_arm(args):
     ms_e2e = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2)], dtype=torch.float64,
                           device=device)
     clock_rec = clocks.stop() if rank == 0 else None
-    # ---- roofline of the dominant kernel (k_hmc_step), timed per launch on its stream ---------
+    # ---- tuner off (set_eval_mode(True)): same chain without the step-size update ----
+    op.set_eval_mode(True)
+    for _ in range(2):
+        ais.sample_and_log_weights(B_global)
+    barrier()
+    ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for s_, e_ in ev3:
+        flush.fill_(1.0)
+        s_.record()
+        ais.sample_and_log_weights(B_global)
+        e_.record()
+    barrier()
+    ms_eval = torch.tensor([sum(a.elapsed_time(b) for a, b in ev3) / len(ev3)], dtype=torch.float64, device=device)
+    op.set_eval_mode(False)
+    # ---- roofline of the dominant kernel (the fused HMC step), timed per launch on its stream ----
     op.chain_noise_override = None
     k_ms = ais.time_transitions(B_global, repeats=2)
     k_ms_t = torch.tensor([k_ms], dtype=torch.float64, device=device)
+    # ---- N > 1: global ESS trigger + global systematic resample, checked against one device -------
+    multi = None
     if world > 1:
+        multi = multi_gpu_parity(ais, B_global, device, group, rank, world)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(k_ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_eval, op=dist.ReduceOp.MAX)
     total_ms, total_e2e_ms, kernel_ms = float(ms), float(ms_e2e), float(k_ms_t)
     if rank == 0:
         peaks = measured_peaks()
@@ -334,42 +403,110 @@ def run_gpu_arm(args):
         sm_mhz = (clock_rec or {}).get("sm_max_mhz") or peaks["sm_max_mhz"]
         n_sm = torch.cuda.get_device_properties(device).multi_processor_count
         ffma_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
-        # ceiling of the engine actually used: warp-level mma.sync m16n8k8 TF32 issues once per
-        # 8 cycles per SM sub-partition (measured, profiles/microbench_hmma.cu) = 2048 FLOP; the
-        # fp32-grade 3xTF32 scheme spends three such MMAs per algorithmic one
-        hmma_tf32_peak = n_sm * 4 * 2048 / 8 * sm_mhz * 1e6 / 1e12
+        rowtile = flow.use_rowtile(B_local)
+        if rowtile:
+            # tcgen05 kind::f16, cta_group::2: 8192 FLOP/cycle/SM measured (profiles/r02_mb_umma_rates.log);
+            # the fp32-grade split spends three f16 MMAs per algorithmic one, and a CTA pair carries 128
+            # particles, so B_local / 64 SMs can be busy (sequential chain per particle)
+            busy_sm = min(n_sm, 2 * ((B_local + 127) // 128))
+            pipe_peak = busy_sm * 8192 * sm_mhz * 1e6 / 1e12 / 3
+            kernel, pipe = "k_hmc_step_u", (f"tcgen05.mma kind::f16 cta_group::2, f16 hi/lo split x3 (fp32-grade), "
+                                            f"{busy_sm} of {n_sm} SMs carry row tiles at this batch")
+        else:
+            pipe_peak = n_sm * 4 * 2048 / 8 * sm_mhz * 1e6 / 1e12 / 3
+            kernel, pipe = "k_hmc_step", "mma.sync m16n8k8 tf32 x3 (fp32-grade split), 14 particles per SM"
         roof = dict(bound="tensor", achieved=achieved, peak=peaks["bf16_tflops_sustained"],
                     unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"], traffic=profiled_traffic(),
-                    kernel="k_hmc_step", kernel_ms=kernel_ms, peak_source=peaks["source"] +
+                    kernel=kernel, kernel_ms=kernel_ms, peak_source=peaks["source"] +
                     " bf16_tflops_sustained (kernel timed inside a long step)",
-                    pipe="mma.sync m16n8k8 tf32 x3 (fp32-grade split)", pipe_peak=hmma_tf32_peak / 3,
-                    pipe_frac=achieved / (hmma_tf32_peak / 3), fp32_ffma_peak=ffma_peak,
+                    pipe=pipe, pipe_peak=pipe_peak, pipe_frac=achieved / pipe_peak, fp32_ffma_peak=ffma_peak,
                     flops_per_launch=flops_per_launch,
-                    note="14 particles per CTA (2048 over 148 SMs, sequential chain) rule out 128-row "
-                         "tcgen05 tiles; GEMMs run as 3xTF32 on the warp-level tensor path to hold the "
-                         "1e-5 fp32 parity bar. frac is vs the measured bf16 cuBLAS peak as required; "
-                         "pipe_frac is vs the measured HMMA TF32 issue rate / 3 (DESIGN.md §4)")
+                    note="algorithmic FLOPs = 2 F_f L B (SURVEY 8d); frac is vs the measured bf16 cuBLAS peak as "
+                         "required; pipe_frac is vs the ceiling of the engine and of the SMs this batch can "
+                         "occupy (DESIGN.md 4: the chain is sequential per particle and 2048 particles are 16 "
+                         "row tiles of 128)")
         launches_per_step = 1 + 3 + 2 + cfg["M"] * cfg["n_outer"] * (2 if world > 1 else 1) + 3 + 2
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=WORKLOAD, global_batch=B_global, l2_flush_between_steps=True,
-                                tuner="on", cuda_graph=bool(ais.use_cuda_graph and world == 1), **{k: cfg[k] for k in ("dim", "n_layers", "M", "L", "n_outer")}),
+                    config=config_block(cfg, world),
+                    engine=dict(hmc_step="row-tile tcgen05 (f16 hi/lo operands, fp32 accumulate)" if rowtile
+                                else "warp-level mma.sync 3xTF32 (weights rounded to 22 bits)",
+                                cuda_graph=bool(ais.use_cuda_graph and world == 1)),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d * world,
                              d2h_bytes_per_step=d2h * world, ms_per_step=total_e2e_ms / args.steps),
                     gpu_launches=launches_per_step * args.steps, clocks=clock_rec, roofline=roof,
+                    eval_mode=dict(ms_per_step=float(ms_eval), value=B_global / (float(ms_eval) * 1e-3),
+                                   note="set_eval_mode(True): tuner off, 5 timed steps"),
                     log_Z_last_timed_call=info["log_Z"], ess_ais_last_timed_call=info["ess_ais"])
+        if multi is not None:
+            line["multi_gpu_parity"] = multi
         if world == 1 and not args.no_cpu_baseline:
-            ts, cinfo = time_cpu_port(cfg, B_local, steps=2, warmup=1)
+            ts, cinfo, kind = time_cpu(cfg, B_local, steps=2, warmup=1)
             cv = B_local * len(ts) / float(np.sum(ts))
+            ts64, _, _ = time_cpu(cfg, B_local, steps=1, warmup=0, dtype=torch.float64)
             line["cpu_baseline"] = dict(
-                value=cv, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"2 timed + 1 warm-up full sample_and_log_weights({B_local}) calls, fp32, "
-                       f"{float(np.sum(ts)):.1f} s of CPU work")
+                value=cv, unit=UNIT, cores=torch.get_num_threads(), kind=kind,
+                sample=f"2 timed + 1 warm-up full sample_and_log_weights({B_local}) calls through the "
+                       f"{'unmodified reference classes (baseline/_ref)' if kind == 'reference' else 'oracle port'}, "
+                       f"fp32, {float(np.sum(ts)):.1f} s of CPU work",
+                fp64_value=B_local / float(ts64[0]),
+                fp64_note="the reference's default dtype (many_well.yaml:41): 1 timed call, no warm-up")
             line["parity"] = parity_leg(cfg, B_local, device)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_parity(ais, B_global, device, group, rank, world):
+    """Untimed check on N > 1 GPUs (BASELINE config 3): the rank-sharded chain with the all-reduced
+    ESS and the global systematic resample must equal the single-device answer bit for bit.  Every
+    rank holds the same pre-drawn noise for the GLOBAL batch; rank 0 also runs the whole batch alone."""
+    import torch.distributed as dist
+    import fab_torch_b200 as fb
+    from fab_torch_b200.resample import systematic_resample
+    cfg = CFG
+    M, d, no = cfg["M"], cfg["dim"], cfg["n_outer"]
+    g = torch.Generator().manual_seed(99)
+    eps = torch.randn(B_global, d, generator=g)
+    mom = torch.randn(M, no, B_global, d, generator=g)
+    exp = torch.empty(M, no, B_global).exponential_(1.0, generator=g)
+    B_local = B_global // world
+    sl = slice(rank * B_local, (rank + 1) * B_local)
+    op = ais.transition_operator
+    op.set_eval_mode(True)                      # identical tuner state on both sides
+    ais.set_next_noise(eps[sl].contiguous(), mom[:, :, sl].contiguous(), exp[:, :, sl].contiguous())
+    pt, lw = ais.sample_and_log_weights(B_global)
+    info = ais.get_logging_info()
+    pt_r, lw_r, did = ais.resample_if_ess_below(pt, lw, threshold=1.1, u0=12345)   # always triggers
+    out = dict(ess_ais_global=info["ess_ais"], log_Z_global=info["log_Z"], resampled=bool(did))
+    # gather the sharded result on rank 0 and compare with a single-device run of the global batch
+    sizes = torch.tensor([lw.shape[0]], device=device)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    if any(int(t.item()) != B_local for t in all_sizes):       # NaN filter shrank a shard: not expected here
+        out["skipped"] = "ragged shards after the NaN filter"
+        op.set_eval_mode(False)
+        return out
+    xs = [torch.empty_like(pt_r.x) for _ in range(world)]
+    ws = [torch.empty_like(lw) for _ in range(world)]
+    dist.all_gather(xs, pt_r.x.contiguous(), group=group)
+    dist.all_gather(ws, lw.contiguous(), group=group)
+    if rank == 0:
+        flow1, target1, op1, ais1 = build_gpu(cfg, device, None)
+        ais1.use_cuda_graph = False
+        op1.set_eval_mode(True)
+        ais1.set_next_noise(eps, mom, exp)
+        pt1, lw1 = ais1.sample_and_log_weights(B_global)
+        info1 = ais1.get_logging_info()
+        pt1_r, lw1_r, _ = ais1.resample_if_ess_below(pt1, lw1, threshold=1.1, u0=12345)
+        out.update(log_w_bit_equal=bool(torch.equal(torch.cat(ws), lw1)),
+                   resampled_x_bit_equal=bool(torch.equal(torch.cat(xs), pt1_r.x)),
+                   ess_abs_diff=abs(info["ess_ais"] - info1["ess_ais"]),
+                   log_Z_abs_diff=abs(info["log_Z"] - info1["log_Z"]))
+    op.set_eval_mode(False)
+    dist.barrier()
+    return out
 
 
 def main():

@@ -294,7 +294,7 @@ class HamiltonianMonteCarlo(TransitionOperator):
             b.exponential_(1.0)
 
     def run(self, point: Point, i: int, beta, log_w: Optional[torch.Tensor] = None,
-            w_update=None, n_active: Optional[torch.Tensor] = None, noise=None) -> Point:
+            w_update=None, n_active: Optional[torch.Tensor] = None, noise=None, timings=None) -> Point:
         """One HMC transition at distribution i.  `w_update=(g_w, g_next)` (the sampler's gammas at
         beta_i and beta_{i+1}) fuses the AIS log-weight update log_w += g_next(x) - g_w(x)
         (ais.py:93-100) into the last outer step.  `noise` = pre-drawn (momentum, exponential)."""
@@ -332,6 +332,9 @@ class HamiltonianMonteCarlo(TransitionOperator):
                                 self.target_p_accept, self.max_grad, g,
                                 1 if (fuse_w and last) else 0, g_w, g_next, 1 if world > 1 else 0)
             prop_out = null_pt if last else _lib.point_ptrs(self._prop_point(point, no & 1))
+            if timings is not None:       # bench.py roofline: brackets the fused kernel only
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = step(flow.desc(), _lib.ptr(blob), tdesc, st, args,
                       _lib.point_ptrs(point), prop_in, prop_out,
                       _lib.ptr(log_w) if log_w is not None else None,
@@ -339,6 +342,9 @@ class HamiltonianMonteCarlo(TransitionOperator):
                       _lib.ptr(n_active) if n_active is not None else None,
                       _lib.ptr(self._stats), _lib.ptr(ws), n, stream)
             _lib.check(rc, "fab_hmc_step_umma_f32" if rowtile else "fab_hmc_step_f32")
+            if timings is not None:
+                e1.record()
+                timings.append((e0, e1))
             if world > 1:
                 fdist.reduce_stats(self._stats[:4], self.process_group)
                 _lib.check(L.fab_hmc_finish_f32(st, args, _lib.ptr(self._stats), stream),
