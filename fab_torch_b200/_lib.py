@@ -172,6 +172,15 @@ def f32(t: torch.Tensor) -> torch.Tensor:
 
 
 def stream_ptr(device=None) -> int:
+    """Current stream of `device`.  The kernels launch on the CURRENT CUDA device, so a tensor on
+    another device than the current one is refused here instead of failing inside the launch."""
+    if device is not None:
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+            raise RuntimeError(
+                f"fab_torch_b200: tensors live on cuda:{dev.index} but the current device is "
+                f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device({dev.index}) (one process "
+                "per GPU) or wrap the call in `with torch.cuda.device(...)`")
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -194,9 +194,18 @@ class AnnealedImportanceSampler:
         dev = flow._device()
         d, M = flow.dim, self.n_intermediate_distributions
         blob = flow.blob()                                   # repacked in place if parameters changed
+        # everything the captured launches bake in: raw pointers of the weight images, of the
+        # operator's state buffers and of the target tables, and the scalar hyper-parameters
+        state_ptrs = tuple(b.data_ptr() for b in op.buffers())
+        tdesc = self._target.target_desc(dev)
+        tkey = tuple(getattr(tdesc, f) for f, _ in tdesc._fields_)
+        hyper = tuple(getattr(op, k, None) for k in ("L", "n_outer", "max_grad", "target_p_accept",
+                                                     "n_updates", "target_prob_accept"))
+        ukey = flow.umma_blob().data_ptr() if flow.use_rowtile(local) else 0
         key = (local, logging, self.p_target, self.alpha, op.p_target, op.alpha,
                bool(getattr(op, "eval_mode", False)), getattr(op, "adjust_step_size", None),
-               blob.data_ptr(), id(op), str(dev))
+               blob.data_ptr(), ukey, id(op), str(dev), state_ptrs, tkey, hyper,
+               _lib.engine_choice())
         ent = self._graphs.get(key)
         if ent is None:
             ent = dict(eps=torch.empty(local, d, dtype=torch.float32, device=dev),
@@ -274,9 +283,17 @@ class AnnealedImportanceSampler:
         torch.cuda.current_stream(dev).synchronize()               # the one sync of the call
         h = self._host.numpy()
         n_init, n_end = int(h[0]), int(h[1])
-        if n_init == 0:
+        g_init, g_end = n_init, n_end
+        if world > 1:
+            # the reference decides on the WHOLE batch (ais.py:202-204); deciding per shard would let
+            # one rank raise while the others wait in the next collective
+            import torch.distributed as dist
+            tot = torch.tensor([n_init, n_end], dtype=torch.int64, device=dev)
+            dist.all_reduce(tot, group=self.process_group)
+            g_init, g_end = int(tot[0]), int(tot[1])
+        if g_init == 0:
             raise Exception("No valid points generated in sampling the chain init")
-        if n_end == 0:
+        if g_end == 0:
             raise Exception("No valid points generated in sampling the chain end")
         if n_init != local:
             print(f"{local - n_init} nan/inf samples/log-probs/log-weights encountered at chain init.")
@@ -319,7 +336,10 @@ class AnnealedImportanceSampler:
                 point.log_q = log_q0.detach()
             base_log_w = point.log_p - log_q0
             ok = torch.isfinite(point.log_p) & torch.isfinite(point.log_q)
-            if bool(ok.any()) and not bool(ok.all()):
+            if not bool(ok.any()):              # ais.py:202-204 (raise_exception=True at chain init)
+                raise Exception("No valid points generated in sampling the chain init")
+            if not bool(ok.all()):
+                print(f"{int((~ok).sum())} nan/inf samples/log-probs/log-weights encountered at chain init.")
                 point, base_log_w = point[ok], base_log_w[ok]
                 point = Point(*(None if t is None else t.contiguous() for t in
                                 (point.x, point.log_q, point.log_p, point.grad_log_q,
@@ -331,7 +351,10 @@ class AnnealedImportanceSampler:
             for j in range(1, self.n_intermediate_distributions + 1):
                 point, log_w = self.perform_transition(point, log_w, j)
             ok = torch.isfinite(point.log_p) & torch.isfinite(point.log_q)
-            if bool(ok.any()) and not bool(ok.all()):
+            if not bool(ok.any()):              # raise_exception=False at chain end (ais.py:177-178)
+                print("No valid points generated in sampling the chain end")
+            elif not bool(ok.all()):
+                print(f"{int((~ok).sum())} nan/inf samples/log-probs/log-weights encountered at chain end.")
                 point, log_w = point[ok], log_w[ok]
             ais_samples.append(point.x.detach().cpu())
             ais_log_w.append(log_w.detach().cpu())

@@ -29,15 +29,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 constexpr int kMaxSmemBytes = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+int sm_count() {                 // per device: a process may hold several GPUs
+    static int cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
     }
-    return n;
+    return cache[dev];
 }
 
 bool flow_ok(const fab_flow_desc* f) {

@@ -334,7 +334,9 @@ __global__ void k_resample_search(const unsigned long long* __restrict__ cdf, lo
         const long long mid = (lo + hi) >> 1;
         if ((unsigned __int128)cdf[mid] * scale > thr) hi = mid; else lo = mid + 1;
     }
-    anc[k] = lo;
+    // S == 0 (no finite log-weight at all): the search runs off the end; keep the identity map
+    // instead of an out-of-range ancestor (the host raises on this state, resample.py)
+    anc[k] = S == 0 ? k : (lo < n ? lo : n - 1);
 }
 
 __global__ void k_gather_rows(const float* __restrict__ src, float* __restrict__ dst,

@@ -511,39 +511,40 @@ __device__ __forceinline__ void ue_epi_hidden(const ULayout& L, UCw& c, uint32_t
     float s, inv_s;
     ue_scale_of<FWD>(m, s, inv_s);          // forward operands are the biased ones
     inv_s_out = inv_s;
-    const float sc = cf * s;                 // un-scale and re-scale in one (s is a power of two)
+    // un-scale, compensate and re-scale with one factor: s and cf are powers of two, (1 + dl) is a
+    // few ulp for these long chains (for the short z-path chain dl is below one ulp and goes through
+    // an FMA instead: ue_acc8 / ue_acc16)
+    const float sc = cf * s * (1.0f + dl);
     uint8_t* hp = ue_smem + L.s_h;
     uint32_t nm[3] = {0u, 0u, 0u};
-    // pass 2 in batches of two chunks: loads of a batch first, one wait, then scale / split / store
+    // pass 2, software-pipelined over the chunks of 16 columns: the loads of chunk j+1 are in flight
+    // while chunk j is scaled / split / stored (tcgen05.wait::ld waits for everything outstanding, so
+    // the next loads are issued right AFTER the wait)
+    uint32_t a[2][16], b[2][16];
+    ue_ld16(ta_main, a[0]);
+    ue_ld16(ta_cross, b[0]);
 #pragma unroll
-    for (int j0 = 0; j0 < NCH; j0 += 2) {
-        uint32_t a[2][16], b[2][16];
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) if (j0 + jj < NCH) {
-            ue_ld16(ta_main + 16 * (j0 + jj), a[jj]);
-            ue_ld16(ta_cross + 16 * (j0 + jj), b[jj]);
-        }
+    for (int j = 0; j < NCH; ++j) {
         umma::tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) if (j0 + jj < NCH) {
-            const int j = j0 + jj;
-            const uint32_t mw = FWD ? 0u : mask[j >> 1] >> (16 * (j & 1));
-            uint32_t bits = 0;
-            float lo8[8], hi8[8];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float t = __uint_as_float(a[jj][i]) + __uint_as_float(b[jj][i]);
-                const float v = fmaf(t, dl, t) * sc;
-                float hv;
-                if (FWD) { const bool on = v > 0.f; bits |= (on ? 1u : 0u) << i; hv = on ? v : 0.f; }
-                else hv = ((mw >> i) & 1u) ? v : 0.f;
-                if (i < 8) lo8[i] = hv; else hi8[i - 8] = hv;
-            }
-            if (FWD) nm[j >> 1] |= bits << (16 * (j & 1));
-            const int chunk = (c.q * L.WQ) / 8 + 2 * j;
-            ue_store_chunk(hp, L.hplane, chunk, c.r, lo8);
-            ue_store_chunk(hp, L.hplane, chunk + 1, c.r, hi8);
+        if (j + 1 < NCH) {
+            ue_ld16(ta_main + 16 * (j + 1), a[(j + 1) & 1]);
+            ue_ld16(ta_cross + 16 * (j + 1), b[(j + 1) & 1]);
         }
+        const uint32_t mw = FWD ? 0u : mask[j >> 1] >> (16 * (j & 1));
+        uint32_t bits = 0;
+        float lo8[8], hi8[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float v = (__uint_as_float(a[j & 1][i]) + __uint_as_float(b[j & 1][i])) * sc;
+            float hv;
+            if (FWD) { const bool on = v > 0.f; bits |= (on ? 1u : 0u) << i; hv = on ? v : 0.f; }
+            else hv = ((mw >> i) & 1u) ? v : 0.f;
+            if (i < 8) lo8[i] = hv; else hi8[i - 8] = hv;
+        }
+        if (FWD) nm[j >> 1] |= bits << (16 * (j & 1));
+        const int chunk = (c.q * L.WQ) / 8 + 2 * j;
+        ue_store_chunk(hp, L.hplane, chunk, c.r, lo8);
+        ue_store_chunk(hp, L.hplane, chunk + 1, c.r, hi8);
     }
     if (FWD) { mask[0] = nm[0]; mask[1] = nm[1]; mask[2] = nm[2]; }
     if (bias_col && c.q == 0) ue_store_one(hp, L.W / 8, c.r, s);

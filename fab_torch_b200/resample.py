@@ -14,6 +14,10 @@ def systematic_ancestors(log_w: torch.Tensor, u0: int) -> torch.Tensor:
     """int64[N] ancestors for offset u0 in [0, 2^32) (position k uses (k + u0/2^32)/N)."""
     lw = _lib.f32(log_w.detach()).contiguous()
     n = lw.shape[0]
+    if not bool(torch.isfinite(lw).any()):
+        # the AIS NaN filter tests log_q / log_p, not log_w (ais.py:190-213): a batch whose
+        # log-weights are all non-finite has no resampling distribution
+        raise ValueError("systematic resampling needs at least one finite log-weight")
     L = _lib.lib()
     ws = torch.empty(int(L.fab_resample_workspace_bytes(n)), dtype=torch.uint8, device=lw.device)
     anc = torch.empty(n, dtype=torch.int64, device=lw.device)

@@ -94,3 +94,69 @@ def test_fab_alpha_div_step_on_device():
     assert base_x.shape == (200, 4) and base_w.shape == (200,)
     assert ais_x.shape == (200, 4) and ais_w.shape == (200,)
     assert base_x.device.type == "cpu"
+
+
+def _gpu_objects(dim=32, K=3, npd=10, M=4):
+    torch.manual_seed(0)
+    flow = fb.B200RealNVP(dim, K, npd)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for k in range(K):
+            lin = flow._nf_model.flows[2 * k].linears[2]
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.01)
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.01)
+    flow = flow.cuda()
+    target = fb.ManyWellEnergy(dim, use_gpu=True)
+    op = fb.HamiltonianMonteCarlo(M, dim, flow.log_prob, target.log_prob, alpha=2.0, p_target=False,
+                                  n_outer=1, epsilon=0.1, L=5).cuda()
+    return flow, target, op
+
+
+@pytest.mark.gpu
+def test_unmodified_fabmodel_runs_on_the_b200_plugin_classes():
+    """The reference's own fab/core.py (baseline/_ref, unmodified) on a GPU, at both insertion levels
+    of INTEGRATION.md: `loss()` = fab_alpha_div (core.py:112-128) with backward, and
+    `get_eval_info()` (core.py:191-220).  Level 1 keeps the reference's Python AIS loop and calls
+    the B200 operator's `transition` once per intermediate distribution; level 2 swaps the sampler."""
+    from oracle.ref_loader import installed_reference_available
+    if not installed_reference_available():
+        pytest.skip("baseline/_ref not installed (run __graft_entry__.build() where /root/reference exists)")
+    load_reference(installed=True)
+    import fab.core
+    M, B = 4, 1024                       # 1024 particles: the row-tile engine under FAB_ENGINE=auto
+    results = {}
+    for level in (1, 2):
+        flow, target, op = _gpu_objects(M=M)
+        orig = fab.core.AnnealedImportanceSampler
+        if level == 2:
+            fab.core.AnnealedImportanceSampler = fb.AnnealedImportanceSampler
+        try:
+            model = fab.core.FABModel(flow=flow, target_distribution=target,
+                                      n_intermediate_distributions=M, transition_operator=op,
+                                      alpha=2.0, loss_type="fab_alpha_div")
+        finally:
+            fab.core.AnnealedImportanceSampler = orig
+        sampler_module = type(model.annealed_importance_sampler).__module__
+        assert sampler_module == ("fab.sampling_methods.ais" if level == 1 else "fab_torch_b200.ais")
+        torch.manual_seed(123)
+        loss = model.loss(B)
+        assert loss.ndim == 0 and torch.isfinite(loss)
+        loss.backward()
+        grads = [p.grad for p in model.parameters()]
+        assert all(g is not None and torch.isfinite(g).all() for g in grads)
+        assert sum(float(g.abs().sum()) for g in grads) > 0
+        assert op._seen_first and op._seen_last            # the fused transitions ran for i = 1..M
+        assert op.p_target is True                          # reset by fab_alpha_div (core.py:126-127)
+        info = model.get_eval_info(outer_batch_size=512, inner_batch_size=256)
+        for key in ("eval_ess_flow", "eval_ess_ais", "flow_test_set_modes_mean_log_prob",
+                    "flow_test_set_exact_mean_log_prob", "flow_forward_kl", "ais_abs_MSE_log_Z_estimate"):
+            assert key in info, (key, sorted(info))
+        assert 0 < info["eval_ess_ais"] <= 1 and 0 < info["eval_ess_flow"] <= 1
+        results[level] = (float(loss), info, model.annealed_importance_sampler.get_logging_info())
+    # the two levels run the same kernels on different random draws: same order of magnitude
+    (l1, i1, log1), (l2, i2, log2) = results[1], results[2]
+    assert abs(log1["log_Z"] - log2["log_Z"]) < 25.0, (log1["log_Z"], log2["log_Z"])
+    # the mode test set is deterministic for dim < 40 (all 2^16 modes): same flow, same number
+    a, b = i1["flow_test_set_modes_mean_log_prob"], i2["flow_test_set_modes_mean_log_prob"]
+    assert abs(a - b) < 1e-4 * abs(a) + 1e-4, (a, b)
+    print(f"\\nlevel 1: loss {l1:.5f} log_Z {log1['log_Z']:.3f} | level 2: loss {l2:.5f} log_Z {log2['log_Z']:.3f}")

@@ -214,3 +214,35 @@ def test_gather_rows_all_forms(rowf, n):
         _lib.check(L.fab_gather_rows_f32(_lib.ptr(s), _lib.ptr(dst), _lib.ptr(anc), n, rowf,
                                          _lib.stream_ptr()))
         assert torch.equal(dst, src[anc])
+
+
+def test_tuner_statistics_survive_a_smaller_batch():
+    """the arrival counter of the cross-CTA reduction sits at a FIXED place in the
+    operator workspace, so a call with a smaller batch (other grid size) after a larger one still
+    produces statistics and tunes."""
+    import fab_torch_b200 as fb
+    from helpers import make_flows, make_manywell
+    for engine in ("warp", "auto"):
+        import os
+        os.environ["FAB_ENGINE"] = engine
+        try:
+            _, _, fp = make_flows(32, 2, 10, last_std=0.02)
+            _, tp = make_manywell(32)
+            op = fb.HamiltonianMonteCarlo(4, 32, fp.log_prob, tp.log_prob, alpha=2.0, epsilon=0.2, L=2).cuda()
+            for n in (2048, 512, 37, 1500):
+                pt = op.create_new_point(torch.randn(n, 32, device="cuda"))
+                eps_before, common_before = op.epsilons.clone(), op.common_epsilon.clone()
+                op._stats.zero_()
+                op.run(pt, 2, 0.5)
+                torch.cuda.synchronize()
+                assert float(op._stats[1]) == float(n), (engine, n, op._stats[:4].tolist())
+                assert not torch.equal(op.epsilons, eps_before) and not torch.equal(op.common_epsilon, common_before)
+        finally:
+            del os.environ["FAB_ENGINE"]
+
+
+def test_resample_without_any_finite_weight_raises():
+    from fab_torch_b200.resample import systematic_ancestors
+    lw = torch.full((64,), float("nan"), device="cuda")
+    with pytest.raises(ValueError):
+        systematic_ancestors(lw, 7)
