@@ -61,10 +61,14 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  Default semantics
+// (.release.cta), as CUTLASS' ClusterBarrier::arrive(cta_id) does for the 2-SM MMA hand-offs: the
+// data these arrivals guard is shared / tensor memory of the ARRIVING CTA, consumed by the tensor
+// core of that same SM, and made visible to it by fence.proxy.async / tcgen05.fence beforehand.
+// (The explicit .release.cluster form compiles to MEMBAR + ERRBAR + CGAERRBAR and was 10 % of the
+// kernel's stall samples: profiles/r02_hot_lines_rowtile.md.)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(smem_u32(bar), rank))
-                 : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(smem_u32(bar), rank)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -79,15 +83,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// acquire at cluster scope: pairs with mbar_arrive_remote of a peer CTA
+// wait on a barrier that peer CTAs arrive on (same instruction as mbar_try_wait; kept as a
+// separate name to mark the cross-CTA hand-offs)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
+    return mbar_try_wait(bar, parity);
 }
 // -DFAB_UMMA_WATCHDOG (bring-up builds): a wait that does not complete within ~2 s traps instead of
 // hanging the GPU, so that a protocol bug shows up as a launch failure.

@@ -489,7 +489,10 @@ __device__ __forceinline__ void ue_epi_hidden(const ULayout& L, UCw& c, uint32_t
                                               uint32_t (&mask)[3], bool bias_col, float& inv_s_out) {
     // pass 1: row maximum from the hi*hi accumulator alone (the cross terms are ~2^-11 of it; the
     // scale only has to put the largest element near 2^13, with a factor 4 of headroom below the
-    // f16 maximum), un-scaled: max(relu(v)) = max(0, max v), cf > 0.  All loads first, one wait.
+    // f16 maximum), un-scaled: max(relu(v)) = max(0, max v), cf > 0.  The backward form takes the
+    // maximum over ALL of the thread's columns, masked or not: an upper bound is all the scale needs
+    // (a masked-out maximum costs a bit or two of the 2^-39 absolute resolution) and it saves the
+    // per-element mask test.  All loads first, one wait.
     float m = 0.f, dummy = 0.f;
     {
         uint32_t a[NCH][16];
@@ -498,12 +501,8 @@ __device__ __forceinline__ void ue_epi_hidden(const ULayout& L, UCw& c, uint32_t
         umma::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-            const uint32_t mw = FWD ? 0u : mask[j >> 1] >> (16 * (j & 1));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (FWD) m = fmaxf(m, __uint_as_float(a[j][i]));
-                else m = fmaxf(m, ((mw >> i) & 1u) ? fabsf(__uint_as_float(a[j][i])) : 0.f);
-            }
+            for (int i = 0; i < 16; ++i) m = fmaxf(m, FWD ? __uint_as_float(a[j][i]) : fabsf(__uint_as_float(a[j][i])));
         }
     }
     m *= cf;

@@ -17,15 +17,19 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "fab_torch_b200", "csrc", "libfab_b200.so")
-KERNEL = "_Z10k_hmc_stepILi16E"
+KERNEL = os.environ.get("FAB_HOT_KERNEL", "_Z10k_hmc_stepILi16E")     # e.g. _Z12k_hmc_step_uILi5E
 
 
 def line_table():
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=d, check=True, capture_output=True)
-        cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True,
-                             text=True).stdout.split("\n")
+        txt = []
+        for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):   # one per translation unit
+            t = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True,
+                               text=True).stdout
+            if ".text." + KERNEL in t:
+                txt = t.split("\n")
+                break
     table, cur, inside = {}, ("?", 0), False
     for l in txt:
         if l.startswith(".text." + KERNEL):
