@@ -769,10 +769,12 @@ __device__ __forceinline__ UEnv ue_setup(const ULayout& L) {
         umma::mbar_init(B.aready, 16);
         umma::mbar_fence_init();
     }
+    __syncthreads();
     if (e.warp == 8) umma::tmem_alloc<2>(slot, 512);
     umma::fence_proxy_async();
     umma::tc_fence_before();
-    umma::cluster_sync_all();
+    __syncthreads();                 // the allocating warp's write of *slot, CTA-wide (as in the guide)
+    umma::cluster_sync_all();        // peer barriers initialised before any remote arrive / multicast commit
     umma::tc_fence_after();
     e.tmem = *slot;
     return e;
