@@ -496,6 +496,8 @@ def multi_gpu_parity(ais, B_global, device, group, rank, world):
         flow1, target1, op1, ais1 = build_gpu(cfg, device, None)
         ais1.use_cuda_graph = False
         op1.set_eval_mode(True)
+        op1.epsilons.copy_(op.epsilons)                 # same (tuned) step sizes on both sides
+        op1.common_epsilon.copy_(op.common_epsilon)
         ais1.set_next_noise(eps, mom, exp)
         pt1, lw1 = ais1.sample_and_log_weights(B_global)
         info1 = ais1.get_logging_info()

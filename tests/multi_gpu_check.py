@@ -42,6 +42,17 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     device = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=device)
+    all_ok = True
+    # the two engines round differently, so the comparison is made per engine (FAB_ENGINE=auto picks
+    # by the LOCAL batch size, which differs between the sharded and the single-device run)
+    for engine in ("warp", "rowtile"):
+        os.environ["FAB_ENGINE"] = engine
+        all_ok = check(rank, world, device, engine) and all_ok
+    dist.destroy_process_group()
+    sys.exit(0 if all_ok else 1)
+
+
+def check(rank, world, device, engine):
     B = 512 * world
     n_loc = B // world
     g = torch.Generator().manual_seed(99)
@@ -93,11 +104,10 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"world={world} B={B}: sharded == single-device: {'PASS' if flag.item() == 1.0 else 'FAIL'}"
+        print(f"[{engine}] world={world} B={B}: sharded == single-device: {'PASS' if flag.item() == 1.0 else 'FAIL'}"
               f"  (log_Z {info_s['log_Z']:.6f} vs {info_1['log_Z']:.6f}, ess_ais {info_s['ess_ais']:.6e} "
-              f"vs {info_1['ess_ais']:.6e})")
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+              f"vs {info_1['ess_ais']:.6e})", flush=True)
+    return flag.item() == 1.0
 
 
 if __name__ == "__main__":
