@@ -187,6 +187,15 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
                          ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
     }
 }
+// cta_group::2 kind::f16 form for warp-uniform issue loops: EVERY lane executes the surrounding code
+// (so the compiler keeps descriptors and addresses in uniform registers) and the instruction itself
+// is predicated on `issue` (true in one elected lane).
+__device__ __forceinline__ void mma_ss2_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t issue) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
 // All MMAs issued so far by this thread arrive (once) on the mbarrier when they complete.
 // CG = 2: the arrive is multicast to the barrier at this offset in every CTA of `cta_mask`.
 template <int CG>

@@ -8,14 +8,30 @@
 //     64 per CTA.  cta_group::2 runs the 64-row half tile of each SM at the full tensor rate
 //     (8172 of 8192 FLOP/cycle/SM measured) and each CTA stages only half of every weight matrix.
 //   * fp32-grade GEMMs from f16 tensor-core products: every operand is split as v*s = hi + lo
-//     (f16 each, s a power of two -- per particle row for activations, per matrix for weights --
-//     chosen so that the largest element sits in [2^13, 2^14)); D = hi*hi + (lo*hi + hi*lo), the
-//     cross terms in their own accumulator, fp32 accumulation in tensor memory.  The tensor core
-//     truncates each accumulation toward zero (measured): the mean shrink, 1.67e-8 per
-//     accumulation of the hi*hi chain for mixed-sign data, is folded into the un-scaling factor.
-//   * Thread (row r, column group q = 0..3) of the 8 compute warps owns columns [q*N/4, (q+1)*N/4)
-//     of every activation of particle r for the whole kernel: the running latent, the momentum and
-//     the gradients live in its registers; only MMA operands pass through shared memory.
+//     (f16 each, s a power of two -- per particle row for activations, per matrix for weights);
+//     D = hi*hi + (lo*hi + hi*lo), the cross terms in their own accumulator, fp32 accumulation in
+//     tensor memory.  The tensor core truncates each accumulation toward zero (measured): the mean
+//     shrink, 1.67e-8 per accumulation of the hi*hi chain for mixed-sign data, is folded into the
+//     un-scaling factor.
+//   * The row scale of a hidden operand is known BEFORE its GEMM has finished: it comes from the
+//     bound |h_n| <= ||h_in||_2 max_n ||W[:,n]||_2 + max|b| (the weight norms are packed with the
+//     images, ||h_in||_2 is accumulated by the epilogue that produced h_in).  The bound is a few
+//     powers of two above the true row maximum -- f16 hi/lo keeps 22 significant bits for every
+//     element within 2^-9 of the largest representable scaled value and 2^-25 absolute below that,
+//     far inside fp32 -- and it removes both the extra pass over the accumulators and the
+//     dependency of one column block's epilogue on the other block.
+//   * MMA / epilogue overlap, in place: a wide GEMM is issued block by block (two blocks of N/2
+//     output columns), block 1 with its k loop split in halves:
+//         (blk0, k-half 0 + bias) | wait A1 | (blk0, k-half 1) (blk1, k-half 0 + bias) -> D0 | (blk1, k-half 1) -> D1
+//     D0 says "block 0 is complete AND nobody reads the first half of the A operand any more", so
+//     the epilogue of block 0 -- which overwrites exactly that half of the operand buffer with the
+//     next GEMM's operand -- runs under the MMAs of (blk1, k-half 1); the epilogue of block 1 runs
+//     under (blk0, k-half 0) of the NEXT GEMM, which the issuer starts as soon as block 0's
+//     columns have been written (A0).  All 8 compute warps work on each block.
+//   * Thread (row r, lane half h, warp half u) owns, in every block, columns [u WQ/2, (u+1) WQ/2)
+//     of lane half h, and columns 8 (2u+h) .. +7 of every d-wide vector for the whole kernel: the
+//     running latent, the momentum and the gradients live in its registers; only MMA operands pass
+//     through shared memory.
 //   * Bias vectors ride in the GEMMs: each biased operand has one extra k-step whose first column
 //     holds the row scale s ("ones" column after un-scaling) and meets the bias row of the weights.
 //   * Saved-for-backward state: (y2, exp(-scale)) of every coupling layer in the 160 tensor-memory
@@ -43,8 +59,13 @@
 // One operand-matrix type of a layer (host-built, include/fab_b200.h documents the blob).
 struct UType {
     int KS;            // k-steps of 16 (incl. the bias step)
+    int KSr;           // k-steps of real weight rows
+    int kfirst;        // k-steps of the first segment in consumption order: k-half 0 (+ bias step); = KS for d-wide inputs
+    int hin;           // 1: the A operand is a hidden activation (written in halves by the previous epilogue)
     int ksps;          // k-steps per pipeline stage
     int R;             // weight rows per CTA and 16-byte k-chunk ( = N: hi and lo rows of N/2 outputs)
+    int Rb;            // rows of one block image per CTA and k-chunk: wide N/2, narrow N
+    int nblk;          // column blocks: wide 2, narrow 1
     int nbh;           // accumulator columns per block: wide N/4, narrow N/2
     int wide;          // 1: two column blocks x three MMAs per k-step; 0: narrow "concat" form
     int a_off, a_lo;   // shared-memory byte offset of the A operand (hi plane), distance to the lo plane
@@ -56,19 +77,54 @@ struct UType {
     long long plain_off, plain_bias_off;   // float offsets inside a layer block of the plain buffer
 };
 
+#define UE_SCAL 16               // floats per layer in the scalar table (see k_umma_scales)
+
+// One entry of the MMA issue program of a layer (host-built by make_ulayout, the same for every layer):
+// `count` consecutive k-steps of one weight stage whose logical k-steps are consecutive too.
+enum : uint32_t {
+    UOP_WAIT_A0 = 1u, UOP_WAIT_A1 = 2u,     // before: wait for the operand halves of the group
+    UOP_NEWSTAGE = 4u,                      // before: the next weight stage (wait full[slot])
+    UOP_WIDE = 8u,                          // three MMAs per k-step (else the narrow two-MMA form)
+    UOP_ACC = 16u,                          // the first k-step accumulates (else it overwrites)
+    UOP_FREE = 32u,                         // after: the stage is consumed (commit empty[slot], next slot)
+    UOP_D0 = 64u, UOP_D1 = 128u             // after: commit dfull[0] / dfull[1] (D1 ends the group)
+};
+struct UOp {
+    uint32_t a;        // A descriptor low word of the first k-step, relative to the shared-memory base >> 4 (LBO included)
+    uint32_t b;        // B descriptor low word relative to the stage base >> 4 (LBO included)
+    uint32_t a_lo;     // distance hi -> lo plane of the A operand >> 4
+    uint32_t kstr;     // B step per k-step >> 4
+    uint32_t d0, d1;   // accumulator columns: wide main / cross, narrow [hi*hi | hi*lo] / += lo*hi
+    uint32_t nbh;      // wide: distance from the hi to the lo rows of the B block >> 4 (rows x 16 B)
+    uint32_t idesc0, idesc1;
+    uint32_t count, flags;
+};
+#define UE_MAX_OPS 48
+
 struct ULayout {
     int d, W, K, WQ;
     UType t[7];
     long long blob_bytes, off_layers, layer_bytes;     // blob: [scalars][layer blocks]
-    int o_loc, o_lsc, o_scal;                           // float offsets in the scalar block; scal[K][8]
+    int o_loc, o_lsc, o_scal;                           // float offsets in the scalar block; scal[K][UE_SCAL]
     long long plain_floats, plain_layer_floats, plain_off_layers;
     long long plain_logs_off;                           // float offset of sum(log_S) inside a plain layer block
-    int s_h, s_z, s_par, s_gv, s_ring, s_ex, s_bar, smem_bytes;
+    int s_h, s_z, s_par, s_gv, s_ring, s_ex, s_ssq, s_bar, smem_bytes;
     int hplane, zplane, pplane;
     float dl[8];     // truncation compensation: [0] v columns of type 0, [1] h1pre of type 0, [2..7] types 1..6
+    int n_ops_fwd, n_ops;      // issue program: ops[0, n_ops_fwd) forward groups of a layer, [n_ops_fwd, n_ops) gradient groups
+    UOp ops[UE_MAX_OPS];
 };
 
 __host__ inline bool umma_supported(int d, int W, int K) { return d == 32 && W % 64 == 0 && W >= 64 && W <= 320 && K >= 1 && K <= 10; }
+
+// logical k-step of the j-th k-step in consumption order: [k-half 0 | bias step | k-half 1]
+__host__ __device__ __forceinline__ int ue_kstep(const UType& t, int j) {
+    if (!t.hin) return j;
+    const int half = t.KSr / 2;
+    if (j < half) return j;
+    if (t.bias) return j == half ? t.KSr : j - 1;
+    return j;
+}
 
 __host__ inline ULayout make_ulayout(int d, int W, int K) {
     ULayout L{};
@@ -83,27 +139,32 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
     o = (o + 127) & ~127;
     L.s_ring = o; o += UE_NSTAGE * UE_STAGE_BYTES;
     L.s_ex = o; o += 4 * 4 * UE_ROWS * 4 * 2;     // exchange buffers: 4 rotating x [2 values][4 groups][64 rows]
-    L.s_bar = o; o += (2 * UE_NSTAGE + 2) * 8 + 16;
+    L.s_ssq = o; o += 2 * 4 * UE_ROWS * 4;        // per-row partial sums of squares: 2 alternating x [4 threads][64 rows]
+    L.s_bar = o; o += (2 * UE_NSTAGE + 4) * 8 + 16;
     L.smem_bytes = o;
-    auto set = [&](int i, int Kreal, int N, int bias, int wide, int a_off, int a_lo, int dcol) {
+    auto set = [&](int i, int Kreal, int N, int bias, int wide, int hin, int a_off, int a_lo, int dcol) {
         UType& t = L.t[i];
-        t.Kreal = Kreal; t.N = N; t.bias = bias; t.wide = wide;
-        t.KS = Kreal / 16 + (bias ? 1 : 0);
+        t.Kreal = Kreal; t.N = N; t.bias = bias; t.wide = wide; t.hin = hin;
+        t.KSr = Kreal / 16;
+        t.KS = t.KSr + (bias ? 1 : 0);
+        t.kfirst = hin ? t.KSr / 2 + (bias ? 1 : 0) : t.KS;
         t.R = N;
+        t.nblk = wide ? 2 : 1;
+        t.Rb = wide ? N / 2 : N;
         t.nbh = wide ? N / 4 : N / 2;
-        t.ksps = UE_STAGE_BYTES / (t.R * 32);
+        t.ksps = UE_STAGE_BYTES / (t.Rb * 32);
         if (t.ksps > t.KS) t.ksps = t.KS;
         t.a_off = a_off; t.a_lo = a_lo; t.dcol = dcol;
         t.idesc_a = umma::instr_desc(umma::FMT_F16, 128, wide ? N / 2 : 2 * N);
         t.idesc_b = umma::instr_desc(umma::FMT_F16, 128, wide ? N / 2 : N);
     };
-    set(0, d, d + W, 1, 1, L.s_z, zplane, 0);        // z -> [v | h1pre]
-    set(1, W, W, 1, 1, L.s_h, hplane, 0);            // h1 -> h2pre
-    set(2, W, d, 1, 0, L.s_h, hplane, 0);            // h2 -> [shift | scale]
-    set(3, d, W, 0, 1, L.s_par, pplane, 0);          // gparam -> gh2
-    set(4, W, W, 0, 1, L.s_h, hplane, 0);            // gh2 -> gh1
-    set(5, W, d, 0, 0, L.s_h, hplane, 0);            // gh1 -> g (first part)
-    set(6, d, d, 0, 0, L.s_gv, pplane, d);           // gv  -> g (second part)
+    set(0, d, d + W, 1, 1, 0, L.s_z, zplane, 0);        // z -> [v | h1pre]
+    set(1, W, W, 1, 1, 1, L.s_h, hplane, 0);            // h1 -> h2pre
+    set(2, W, d, 1, 0, 1, L.s_h, hplane, 0);            // h2 -> [shift | scale]
+    set(3, d, W, 0, 1, 0, L.s_par, pplane, 0);          // gparam -> gh2
+    set(4, W, W, 0, 1, 1, L.s_h, hplane, 0);            // gh2 -> gh1
+    set(5, W, d, 0, 0, 1, L.s_h, hplane, 0);            // gh1 -> g (first part)
+    set(6, d, d, 0, 0, 0, L.s_gv, pplane, d);           // gv  -> g (second part)
     long long bo = 0, po = 0;
     for (int i = 0; i < 7; ++i) {
         UType& t = L.t[i];
@@ -114,7 +175,7 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
     L.plain_logs_off = po; po += 4;
     L.layer_bytes = bo; L.plain_layer_floats = po;
     L.o_loc = 0; L.o_lsc = d; L.o_scal = 2 * d;
-    L.off_layers = ((2 * d + 8 * K) * 4 + 127) & ~127;
+    L.off_layers = ((2 * d + UE_SCAL * K) * 4 + 127) & ~127;
     L.blob_bytes = L.off_layers + L.layer_bytes * K;
     L.plain_off_layers = 2 * d;
     L.plain_floats = L.plain_off_layers + L.plain_layer_floats * K;
@@ -124,14 +185,64 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
     L.dl[0] = 4.5e-8f;     // calibrated on log q of a 10-layer flow (one FMA rounds up for ~60 % of the mantissas)
     L.dl[1] = UE_TRUNC_PER_ACC * (float)L.t[0].KS;
     for (int i = 1; i < 7; ++i) L.dl[1 + i] = UE_TRUNC_PER_ACC * (float)L.t[i].KS;
+    // ---- MMA issue program (order: header comment "MMA / epilogue overlap"; the weight stages are
+    // consumed in exactly the order ue_for_each_stage produces them) ----
+    int no = 0;
+    auto group = [&](int t0, int t1) {
+        bool first = true, a1 = false;
+        for (int ti = t0; ti <= t1; ++ti) {
+            const UType& t = L.t[ti];
+            // boundaries inside the consumption order where a run must end
+            const int kb0 = t.hin && t.bias ? t.KSr / 2 : t.KS, kb1 = t.hin && t.bias ? kb0 + 1 : t.KS;
+            for (int g = 0; g < t.nblk; ++g)
+                for (int j0 = 0; j0 < t.KS; j0 += t.ksps) {
+                    const int j1 = j0 + t.ksps < t.KS ? j0 + t.ksps : t.KS;
+                    int ja = j0;
+                    while (ja < j1) {
+                        int jb = j1;
+                        if (ja < kb0 && kb0 < jb) jb = kb0;
+                        if (ja < kb1 && kb1 < jb) jb = kb1;
+                        if (ja < t.kfirst && t.kfirst < jb) jb = t.kfirst;
+                        UOp& o = L.ops[no++];
+                        o = UOp{};
+                        o.a = (uint32_t)(t.a_off >> 4) + (uint32_t)ue_kstep(t, ja) * 128u + ((1024u >> 4) << 16);
+                        o.b = (uint32_t)(ja - j0) * (uint32_t)t.Rb * 2u + (((uint32_t)t.Rb * 16u >> 4) << 16);
+                        o.a_lo = (uint32_t)t.a_lo >> 4;
+                        o.kstr = (uint32_t)t.Rb * 2u;
+                        o.nbh = (uint32_t)t.nbh;
+                        o.d0 = t.wide ? (uint32_t)(t.dcol + g * 2 * t.nbh) : (uint32_t)t.dcol;
+                        o.d1 = o.d0 + (uint32_t)t.nbh;
+                        o.idesc0 = t.idesc_a; o.idesc1 = t.wide ? t.idesc_a : t.idesc_b;
+                        o.count = (uint32_t)(jb - ja);
+                        uint32_t f = (t.wide ? UOP_WIDE : 0u) | (ja > 0 ? UOP_ACC : 0u);
+                        if (first) { f |= UOP_WAIT_A0; if (!t.hin) { f |= UOP_WAIT_A1; a1 = true; } first = false; }
+                        if (!a1 && ja >= t.kfirst) { f |= UOP_WAIT_A1; a1 = true; }
+                        if (ja == j0) f |= UOP_NEWSTAGE;
+                        if (jb == j1) f |= UOP_FREE;
+                        // block 0's epilogue may start: hidden input -> after (blk1, k-half 0 + bias), d-wide input -> after blk0
+                        if (t.wide && t.hin && g == 1 && jb == t.kfirst) f |= UOP_D0;
+                        if (t.wide && !t.hin && g == 0 && jb == t.KS) f |= UOP_D0;
+                        if (ti == t1 && g == t.nblk - 1 && jb == t.KS) f |= UOP_D1;
+                        o.flags = f;
+                        ja = jb;
+                    }
+                }
+        }
+    };
+    group(0, 0); group(1, 1); group(2, 2);
+    L.n_ops_fwd = no;
+    group(3, 3); group(4, 4); group(5, 6);
+    L.n_ops = no;
     return L;
 }
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: plain fp32 matrices M[k][n] (+ bias rows) -> per-rank f16 hi/lo stage images
 // ---------------------------------------------------------------------------------------------
-// one block per (layer, type): s_w = 2^e with max|M|,|bias| * s_w in [2^13, 2^14); writes
-// scal[layer][type] = (1 / s_w) * (1 + UE_TRUNC_PER_ACC * KS) and scal[layer][7] = sum(log_S).
+// one block per (layer, type): s_w = 2^e with max|M|,|bias| * s_w in [2^13, 2^14).  Scalar table of a
+// layer (UE_SCAL floats): [0..6] 1 / s_w of the seven types, [7] sum(log_S), [8..11] the column-norm
+// bound max_n ||M[:,n]||_2 of the wide types 0 (h1pre columns only), 1, 3, 4 (the a-priori operand
+// scales of the hidden activations come from it), [12..13] max_n |bias_n| of types 0 and 1.
 __global__ void k_umma_scales(ULayout L, const float* __restrict__ plain, float* __restrict__ blob_f) {
     const int layer = blockIdx.x / 7, ti = blockIdx.x % 7;
     const UType& t = L.t[ti];
@@ -139,27 +250,43 @@ __global__ void k_umma_scales(ULayout L, const float* __restrict__ plain, float*
     const long long cnt = (long long)t.Kreal * t.N + (t.bias ? t.N : 0);
     float m = 0.f;
     for (long long i = threadIdx.x; i < cnt; i += blockDim.x) m = fmaxf(m, fabsf(M[i]));
-    __shared__ float red[32];
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    // column norms (threads walk the columns: coalesced rows) and the largest bias
+    float cn = 0.f, bm = 0.f;
+    if (t.wide) {
+        const int n0 = ti == 0 ? L.d : 0;
+        for (int n = n0 + threadIdx.x; n < t.N; n += blockDim.x) {
+            float ss = 0.f;
+            for (int k = 0; k < t.Kreal; ++k) { const float w = M[(size_t)k * t.N + n]; ss = fmaf(w, w, ss); }
+            cn = fmaxf(cn, ss);
+            if (t.bias) bm = fmaxf(bm, fabsf(M[(size_t)t.Kreal * t.N + n]));
+        }
+    }
+    __shared__ float red[3][32];
+    m = warp_max(m); cn = warp_max(cn); bm = warp_max(bm);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m; red[1][threadIdx.x >> 5] = cn; red[2][threadIdx.x >> 5] = bm; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { m = fmaxf(m, red[0][w]); cn = fmaxf(cn, red[1][w]); bm = fmaxf(bm, red[2][w]); }
         int e = 0;
         if (m > 0.f && m < CUDART_INF_F) { frexpf(m, &e); e = 14 - e; }
         if (e > 30) e = 30;
         if (e < -30) e = -30;
-        float* scal = blob_f + L.o_scal + (size_t)layer * 8;
+        float* scal = blob_f + L.o_scal + (size_t)layer * UE_SCAL;
         scal[ti] = ldexpf(1.f, -e);
-        // the exponent itself, for the pack kernel (scratch behind the scalar table is not available:
-        // recover it there from scal by the same formula)
         if (ti == 0) scal[7] = plain[L.plain_off_layers + (size_t)layer * L.plain_layer_floats + L.plain_logs_off];
+        if (t.wide) {
+            const int wi = ti == 0 ? 0 : ti == 1 ? 1 : ti == 3 ? 2 : 3;
+            scal[8 + wi] = sqrtf(cn) * 1.0001f;        // (upper bound: fp32 rounding of the sum)
+            if (t.bias) scal[12 + wi] = bm;
+        }
     }
     if (blockIdx.x == 0)
         for (int j = threadIdx.x; j < 2 * L.d; j += blockDim.x) blob_f[j] = plain[j];
 }
 
-// one thread per 16-byte chunk of the images: grid.x covers (layer, type, rank, chunk, row)
+// one thread per 16-byte chunk of the images: grid.x covers (rank, block, k-step in consumption
+// order, chunk of the k-step, row).  Image of (type, rank): for each column block the k-step slabs
+// [2 chunks][Rb rows][16 bytes] in the order the MMA issuer consumes them (ue_kstep).
 __global__ void k_umma_pack(ULayout L, const float* __restrict__ plain, uint8_t* __restrict__ blob) {
     const int layer = blockIdx.y, ti = blockIdx.z;
     const UType& t = L.t[ti];
@@ -167,24 +294,25 @@ __global__ void k_umma_pack(ULayout L, const float* __restrict__ plain, uint8_t*
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 2 * per_rank) return;
     const int rank = (int)(idx / per_rank);
-    const long long rem = idx % per_rank;
-    const int c = (int)(rem / t.R), row = (int)(rem % t.R);
+    long long rem = idx % per_rank;
+    const long long per_blk = (long long)t.KS * 2 * t.Rb;
+    const int g = (int)(rem / per_blk);
+    rem %= per_blk;
+    const int slab = (int)(rem / t.Rb), row = (int)(rem % t.Rb);   // slab = 2 j + chunk-of-k-step
+    const int c = 2 * ue_kstep(t, slab >> 1) + (slab & 1);         // logical 16-byte k-chunk
     // row -> (part, output column n)
-    int part, n;
+    const int part = row / t.nbh, i = row % t.nbh;
+    int n;
     if (t.wide) {
-        const int g = row / (2 * t.nbh), r2 = row % (2 * t.nbh);
-        part = r2 / t.nbh;
-        const int i = r2 % t.nbh, q = 2 * g + rank;
+        const int q = 2 * g + rank;
         if (ti == 0) n = i < L.WQ ? L.d + q * L.WQ + i : q * UE_DQ + (i - L.WQ);    // [h1pre cols | v cols]
         else n = q * L.WQ + i;
     } else {
-        part = row / t.nbh;
-        const int i = row % t.nbh;
         n = i < UE_DQ ? rank * UE_DQ + i : L.d / 2 + rank * UE_DQ + (i - UE_DQ);
     }
     const float* blob_f = reinterpret_cast<const float*>(blob);
     // s_w from the scale kernel's output scal = 1 / s_w
-    const float sc = blob_f[L.o_scal + (size_t)layer * 8 + ti];
+    const float sc = blob_f[L.o_scal + (size_t)layer * UE_SCAL + ti];
     const float sw = 1.f / sc;             // both powers of two
     const float* M = plain + L.plain_off_layers + (size_t)layer * L.plain_layer_floats + t.plain_off;
     const float* B = plain + L.plain_off_layers + (size_t)layer * L.plain_layer_floats + t.plain_bias_off;
@@ -199,7 +327,7 @@ __global__ void k_umma_pack(ULayout L, const float* __restrict__ plain, uint8_t*
         out[j] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
     }
     uint8_t* dst = blob + L.off_layers + (size_t)layer * L.layer_bytes + t.blob_off +
-                   (size_t)rank * t.KS * t.R * 32 + ((size_t)c * t.R + row) * 16;
+                   (size_t)rank * t.KS * t.R * 32 + (size_t)g * t.KS * t.Rb * 32 + ((size_t)slab * t.Rb + row) * 16;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
 }
 
@@ -209,9 +337,10 @@ __global__ void k_umma_pack(ULayout L, const float* __restrict__ plain, uint8_t*
 extern __shared__ __align__(1024) uint8_t ue_smem[];
 
 // -DUE_PROF: cycle counters of CTA 0 (compute warp 0 lane 0, the MMA issuer, the producer);
-// read back with fab_umma_prof_read.  0: compute waits for accumulators, 1: compute epilogue work,
-// 2: issuer waits for operands (aready), 3: issuer waits for weight stages, 4: issuer issues,
-// 5: producer waits for free slots, 6: compute barrier/exchange, 7: kernel total (compute warp 0)
+// read back with fab_umma_prof_read.  0: compute waits for D0, 1: compute waits for D1,
+// 2: issuer waits for operands (A0 / A1), 3: issuer waits for weight stages, 4: issuer issues,
+// 5: producer waits for free slots, 6: compute barrier/exchange, 7: flow evaluations (compute warp 0),
+// 8..13: compute waits (D0 + D1) per GEMM group G1, G2, G3, G3T, G2T, G1T
 #ifdef UE_PROF
 __device__ unsigned long long g_ue_prof[16];
 #define UE_T0() const long long ue_t0_ = clock64()
@@ -224,10 +353,13 @@ __device__ unsigned long long g_ue_prof[16];
 // full[s]: stage s has landed -- in the leader CTA it counts two arrivals: its own producer's
 // expect_tx and the peer's relay (so the MMA issuer polls ONE barrier per stage: a try_wait costs
 // ~100 cycles of the single issuing thread even when the phase is already complete).
+// aready[h] (leader CTA, 16 warp arrivals per GEMM group): half h of the group's A operand is written
+// (A0: first half of the k-chunks + the bias chunk; operands that are not written in halves arrive on both).
+// dfull[0]: accumulator block 0 complete and the first operand half no longer read; dfull[1]: group complete.
 struct UBars { uint64_t *full, *empty, *dfull, *aready; };
 __device__ __forceinline__ UBars ue_bars(const ULayout& L) {
     uint64_t* b = reinterpret_cast<uint64_t*>(ue_smem + L.s_bar);
-    return {b, b + UE_NSTAGE, b + 2 * UE_NSTAGE, b + 2 * UE_NSTAGE + 1};
+    return {b, b + UE_NSTAGE, b + 2 * UE_NSTAGE, b + 2 * UE_NSTAGE + 2};
 }
 
 // The GEMM groups of one flow evaluation, in execution order.  f(layer, first type, last type).
@@ -236,119 +368,121 @@ __device__ __forceinline__ void ue_for_each_group(const ULayout& L, bool grad, F
     for (int k = L.K - 1; k >= 0; --k) { f(k, 0, 0); f(k, 1, 1); f(k, 2, 2); }
     if (grad) for (int k = 0; k < L.K; ++k) { f(k, 3, 3); f(k, 4, 4); f(k, 5, 6); }
 }
-
-// warp 9 (warp-uniform loop, one elected lane issues): stream every weight stage of `n_evals` flow evaluations into the ring
-__device__ void ue_producer(const ULayout& L, const uint8_t* __restrict__ blob, uint32_t rank, int n_evals, bool grad) {
-    const UBars B = ue_bars(L);
-    const uint64_t pol = umma::l2_evict_last_policy();
+// The weight stages of `n_evals` evaluations in consumption order: f(type, layer, block, first k-step
+// (consumption index), k-steps in the stage, running stage index)
+template <class F>
+__device__ __forceinline__ void ue_for_each_stage(const ULayout& L, int n_evals, bool grad, F f) {
     uint32_t it = 0;
     for (int ev = 0; ev < n_evals; ++ev)
         ue_for_each_group(L, grad, [&](int k, int t0, int t1) {
             for (int ti = t0; ti <= t1; ++ti) {
                 const UType& t = L.t[ti];
-                const uint8_t* src = blob + L.off_layers + (size_t)k * L.layer_bytes + t.blob_off + (size_t)rank * t.KS * t.R * 32;
-                for (int s0 = 0; s0 < t.KS; s0 += t.ksps) {
-                    const int cnt = min(t.ksps, t.KS - s0);
-                    const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
-                    { UE_T0(); umma::mbar_wait(B.empty + slot, par ^ 1); UE_ACC(5, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
-                    const uint32_t bytes = (uint32_t)cnt * t.R * 32;
-                    if (umma::elect_one()) {
-                        umma::mbar_expect_tx(B.full + slot, bytes);
-                        umma::bulk_g2s(ue_smem + L.s_ring + slot * UE_STAGE_BYTES, src + (size_t)s0 * t.R * 32, bytes, B.full + slot, pol);
-                    }
-                    __syncwarp();
-                    ++it;
-                }
+                for (int g = 0; g < t.nblk; ++g)
+                    for (int j0 = 0; j0 < t.KS; j0 += t.ksps) { f(t, k, g, j0, min(t.ksps, t.KS - j0), it); ++it; }
             }
         });
+}
+
+// warp 9 (warp-uniform loop, one elected lane issues): stream every weight stage of `n_evals` flow evaluations into the ring
+__device__ void ue_producer(const ULayout& L, const uint8_t* __restrict__ blob, uint32_t rank, int n_evals, bool grad) {
+    const UBars B = ue_bars(L);
+    const uint64_t pol = umma::l2_evict_last_policy();
+    ue_for_each_stage(L, n_evals, grad, [&](const UType& t, int k, int g, int j0, int cnt, uint32_t it) {
+        const uint8_t* src = blob + L.off_layers + (size_t)k * L.layer_bytes + t.blob_off + (size_t)rank * t.KS * t.R * 32 +
+                             ((size_t)g * t.KS + j0) * t.Rb * 32;
+        const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
+        { UE_T0(); umma::mbar_wait(B.empty + slot, par ^ 1); UE_ACC(5, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
+        const uint32_t bytes = (uint32_t)cnt * t.Rb * 32;
+        if (umma::elect_one()) {
+            umma::mbar_expect_tx(B.full + slot, bytes);
+            umma::bulk_g2s(ue_smem + L.s_ring + slot * UE_STAGE_BYTES, src, bytes, B.full + slot, pol);
+        }
+        __syncwarp();
+    });
 }
 
 // warp 8 of the peer CTA: tell the leader when this CTA's half of a stage has landed
 __device__ void ue_relay(const ULayout& L, int n_evals, bool grad) {
     const UBars B = ue_bars(L);
-    uint32_t it = 0;
-    for (int ev = 0; ev < n_evals; ++ev)
-        ue_for_each_group(L, grad, [&](int, int t0, int t1) {
-            for (int ti = t0; ti <= t1; ++ti) {
-                const UType& t = L.t[ti];
-                for (int s0 = 0; s0 < t.KS; s0 += t.ksps) {
-                    const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
-                    umma::mbar_wait(B.full + slot, par);
-                    if (umma::elect_one()) umma::mbar_arrive_remote(B.full + slot, 0);
-                    __syncwarp();
-                    ++it;
-                }
-            }
-        });
+    ue_for_each_stage(L, n_evals, grad, [&](const UType&, int, int, int, int, uint32_t it) {
+        const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
+        umma::mbar_wait(B.full + slot, par);
+        if (umma::elect_one()) umma::mbar_arrive_remote(B.full + slot, 0);
+        __syncwarp();
+    });
 }
 
-// warp 8 of the leader CTA: issue the MMAs of the pair.  The whole warp runs the loop and one
-// elected lane issues, so that descriptors and addresses stay in uniform registers (a single-lane
-// code path costs ~45 cycles per tcgen05.mma in compiler-generated elect loops; uniform: 21-40,
-// profiles/r02_mb_umma_rates.log)
+// warp 8 of the leader CTA: issue the MMAs of the pair by running the layer's issue program
+// (ULayout::ops) -- a small table-driven loop: the issuer is a single thread's instruction stream and
+// every instruction between two tcgen05.mma counts (the unrolled control flow of an earlier version
+// was 16 k SASS lines and stalled on instruction fetch).  Every lane executes the loop, the MMAs and
+// commits are predicated on one elected lane, so descriptors and addresses stay in uniform registers.
 __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) {
     const UBars B = ue_bars(L);
-    const uint32_t sbase = umma::smem_u32(ue_smem);
-    uint32_t it = 0, gi = 0;
-    for (int ev = 0; ev < n_evals; ++ev)
-        ue_for_each_group(L, grad, [&](int, int t0, int t1) {
-            { UE_T0(); umma::mbar_wait_cluster(B.aready, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
-            umma::tc_fence_after();
-            for (int ti = t0; ti <= t1; ++ti) {
-                const UType& t = L.t[ti];
-                const uint32_t lbo_b = (uint32_t)t.R * 16;
-                for (int s0 = 0; s0 < t.KS; s0 += t.ksps) {
-                    const int cnt = min(t.ksps, t.KS - s0);
-                    const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
-                    { UE_T0(); umma::mbar_wait_cluster(B.full + slot, par); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0); }
-                    umma::tc_fence_after();
-                    UE_T0();
-                    // descriptors: high word constant (SBO = 128 B, version 1), low word = addr >> 4 | LBO >> 4 << 16
-                    const uint32_t sb = sbase + L.s_ring + slot * UE_STAGE_BYTES;
-                    const uint32_t dhi = (128u >> 4) | (1u << 14);
-                    const uint32_t alo = ((sbase + t.a_off) >> 4) | ((1024u >> 4) << 16), alo_d = (uint32_t)t.a_lo >> 4;
-                    const uint32_t blo = (sb >> 4) | ((lbo_b >> 4) << 16), kstr = (uint32_t)t.R * 2;   // 32 R bytes per k-step
-                    auto desc = [&](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
-                    const bool leader_lane = umma::elect_one();
-                    if (leader_lane)
-                    for (int j = 0; j < cnt; ++j) {
-                        const int ks = s0 + j;
-                        const uint64_t dah = desc(alo + ks * 128), dal = desc(alo + alo_d + ks * 128);
-                        const uint32_t bk = blo + (uint32_t)j * kstr;
-                        const bool acc = ks > 0;
-                        if (t.wide) {
-#pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-                                const uint64_t dbh = desc(bk + (uint32_t)(g * 2 * t.nbh)), dbl = desc(bk + (uint32_t)(g * 2 * t.nbh + t.nbh));
-                                const uint32_t dm = tmem + t.dcol + g * t.nbh, dx = dm + 2 * t.nbh;
-                                umma::mma_ss<2, true>(dx, dal, dbh, t.idesc_a, acc);
-                                umma::mma_ss<2, true>(dx, dah, dbl, t.idesc_a, true);
-                                umma::mma_ss<2, true>(dm, dah, dbh, t.idesc_a, acc);
-                            }
-                        } else {
-                            const uint64_t db = desc(bk);
-                            umma::mma_ss<2, true>(tmem + t.dcol, dah, db, t.idesc_a, acc);               // [hi*hi | hi*lo]
-                            umma::mma_ss<2, true>(tmem + t.dcol + t.nbh, dal, db, t.idesc_b, true);      // += lo*hi
-                        }
-                    }
-                    if (leader_lane) umma::mma_commit<2>(B.empty + slot, 3);
-                    __syncwarp();
-                    UE_ACC(4, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
-                    ++it;
-                }
+    const uint32_t sbase4 = umma::smem_u32(ue_smem) >> 4, ring4 = (umma::smem_u32(ue_smem) + L.s_ring) >> 4;
+    const uint32_t dhi = (128u >> 4) | (1u << 14);        // descriptor high word: SBO = 128 B, version 1
+    auto desc = [&](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
+    const uint32_t lead = umma::elect_one() ? 1u : 0u;      // the lane whose MMAs and commits are issued
+    uint32_t it = 0, gi = 0, sb4 = 0;
+    auto run = [&](int e0, int e1) {
+        for (int e = e0; e < e1; ++e) {
+            const UOp& o = L.ops[e];
+            const uint32_t f = o.flags;
+            if (f & UOP_WAIT_A0) {
+                UE_T0(); umma::mbar_wait_cluster(B.aready, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
             }
-            if (umma::elect_one()) umma::mma_commit<2>(B.dfull, 3);
+            if (f & UOP_WAIT_A1) {
+                UE_T0(); umma::mbar_wait_cluster(B.aready + 1, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
+            }
+            if (f & UOP_NEWSTAGE) {
+                const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
+                UE_T0(); umma::mbar_wait_cluster(B.full + slot, par); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
+                sb4 = ring4 + slot * (UE_STAGE_BYTES >> 4);
+            }
+            if (f & (UOP_WAIT_A0 | UOP_WAIT_A1 | UOP_NEWSTAGE)) umma::tc_fence_after();
+            {
+                UE_T0();
+                uint32_t ah = sbase4 + o.a, bk = sb4 + o.b, acc = (f & UOP_ACC) ? 1u : 0u;
+                const uint32_t al = o.a_lo, kstr = o.kstr, d0 = tmem + o.d0, d1 = tmem + o.d1, id0 = o.idesc0, id1 = o.idesc1, nbh = o.nbh;
+                if (f & UOP_WIDE) {
+                    for (uint32_t n = o.count; n > 0; --n) {
+                        umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id0, acc, lead);           // cross  = lo * hi
+                        umma::mma_ss2_pred(d1, desc(ah), desc(bk + nbh), id0, 1u, lead);           // cross += hi * lo
+                        umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // main   = hi * hi
+                        ah += 128; bk += kstr; acc = 1u;
+                    }
+                } else {
+                    for (uint32_t n = o.count; n > 0; --n) {
+                        umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // [hi*hi | hi*lo]
+                        umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id1, 1u, lead);            // += lo*hi
+                        ah += 128; bk += kstr; acc = 1u;
+                    }
+                }
+                UE_ACC(4, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
+            }
+            if (f & UOP_FREE) {
+                if (lead) umma::mma_commit<2>(B.empty + (it % UE_NSTAGE), 3);
+                ++it;
+            }
+            if (f & UOP_D0) { if (lead) umma::mma_commit<2>(B.dfull, 3); }
+            if (f & UOP_D1) { if (lead) umma::mma_commit<2>(B.dfull + 1, 3); ++gi; }
             __syncwarp();
-            ++gi;
-        });
+        }
+    };
+    for (int ev = 0; ev < n_evals; ++ev) {
+        for (int k = 0; k < L.K; ++k) run(0, L.n_ops_fwd);
+        if (grad) for (int k = 0; k < L.K; ++k) run(L.n_ops_fwd, L.n_ops);
+    }
 }
 
 // ---- compute warps --------------------------------------------------------------------------------
 struct UCw {
-    int r, q, g, h;             // row, column group (2g + h), block, half
+    int r, q, g, h;             // row, d-column group (2g + h), warp half, lane half
     uint32_t tl;                // tensor-memory lane base of the warp << 16
-    uint32_t gi;                // GEMM groups consumed so far (phase of dfull)
+    uint32_t gi;                // GEMM groups consumed so far (phase of dfull[1])
+    uint32_t n0;                // wide GEMM groups consumed so far (phase of dfull[0]: only wide groups commit it)
     uint32_t xb;                // rotating exchange buffer index
+    uint32_t nq;                // sum-of-squares hand-offs so far (alternating buffer)
     uint32_t tmem;
     uint32_t rank;
 };
@@ -384,11 +518,23 @@ __device__ __forceinline__ void ue_row_sum2(const ULayout& L, UCw& c, float& a, 
     const float* e2 = ex + 4 * UE_ROWS;
     b = ((e2[c.r] + e2[UE_ROWS + c.r]) + e2[2 * UE_ROWS + c.r]) + e2[3 * UE_ROWS + c.r];
 }
-// power-of-two operand scale: row maximum -> [2^13, 2^14).  BIASED operands carry s itself as an f16
-// number (the "ones" column), so s <= 2^15 there (rows whose maximum is below 2^-2 keep a smaller
-// scaled maximum, still far above the f16 subnormals); a row maximum above 2^38 makes the ones
-// column underflow, i.e. drops a bias that is < 1e-11 of the row.  Gradient operands are un-biased
-// and take the full exponent range (tiny or huge gradient rows keep 22 significant bits).
+// Sum of squares of a hidden operand row, handed from the epilogue that wrote the operand to the
+// epilogue of the GEMM that consumes it (no barrier: the consumer runs after accumulators that
+// every writer's operand-ready arrival precedes; two alternating buffers keep a fast thread's next
+// hand-off away from a slow thread's read).
+__device__ __forceinline__ void ue_ssq_put(const ULayout& L, UCw& c, float v) {
+    reinterpret_cast<float*>(ue_smem + L.s_ssq)[(c.nq & 1) * (4 * UE_ROWS) + c.q * UE_ROWS + c.r] = v;
+}
+__device__ __forceinline__ float ue_ssq_get(const ULayout& L, UCw& c) {
+    const float* p = reinterpret_cast<const float*>(ue_smem + L.s_ssq) + (c.nq & 1) * (4 * UE_ROWS) + c.r;
+    ++c.nq;
+    return ((p[0] + p[UE_ROWS]) + p[2 * UE_ROWS]) + p[3 * UE_ROWS];
+}
+// power-of-two operand scale: m (the row maximum or an upper bound of it) -> [2^13, 2^14).  BIASED
+// operands carry s itself as an f16 number (the "ones" column), so s <= 2^15 there (rows whose bound
+// is below 2^-2 keep a smaller scaled maximum, still far above the f16 subnormals); a bound above
+// 2^38 makes the ones column underflow, i.e. drops a bias that is < 1e-11 of the row.  Gradient
+// operands are un-biased and take the full exponent range.
 template <bool BIASED>
 __device__ __forceinline__ void ue_scale_of(float m, float& s, float& inv_s) {
     int es = 0;
@@ -422,17 +568,25 @@ __device__ __forceinline__ void ue_store_chunk(uint8_t* hi_plane, int a_lo, int 
 __device__ __forceinline__ void ue_store_one(uint8_t* hi_plane, int chunk, int r, float s) {
     *reinterpret_cast<__half*>(hi_plane + (size_t)chunk * (UE_ROWS * 16) + r * 16) = __float2half_rn(s);
 }
-// operand complete: make it visible to the tensor core and release the MMA issuer (one arrive per warp)
-__device__ __forceinline__ void ue_operand_ready(const ULayout& L) {
+// operand (half) complete: make it visible to the tensor core and release the MMA issuer (one arrive
+// per warp).  which = 0 / 1: that half; 2: both (operands written in one go)
+__device__ __forceinline__ void ue_operand_ready(const ULayout& L, int which) {
     umma::fence_proxy_async();
     umma::tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) umma::mbar_arrive_remote(ue_bars(L).aready, 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (which != 1) umma::mbar_arrive_remote(ue_bars(L).aready, 0);
+        if (which != 0) umma::mbar_arrive_remote(ue_bars(L).aready + 1, 0);
+    }
 }
-// wait for the accumulators of the next GEMM group
-__device__ __forceinline__ void ue_wait_acc(const ULayout& L, UCw& c) {
-    { UE_T0(); umma::mbar_wait(ue_bars(L).dfull, c.gi & 1); UE_ACC(0, blockIdx.x == 0 && threadIdx.x == 0); }
-    ++c.gi;
+// wait for accumulator barrier `which` of the current GEMM group
+__device__ __forceinline__ void ue_wait_acc(const ULayout& L, UCw& c, int which) {
+    UE_T0();
+    umma::mbar_wait(ue_bars(L).dfull + which, (which ? c.gi : c.n0) & 1);
+    UE_ACC(which, blockIdx.x == 0 && threadIdx.x == 0);
+    // per GEMM group of a value+gradient evaluation (counters 8..13: G1, G2, G3, G3T, G2T, G1T)
+    UE_ACC(8 + ((int)(c.gi % (6 * L.K)) < 3 * L.K ? (int)(c.gi % (6 * L.K)) % 3 : 3 + (int)(c.gi % (6 * L.K) - 3 * L.K) % 3),
+           blockIdx.x == 0 && threadIdx.x == 0);
     umma::tc_fence_after();
 }
 // v = (main + cross) (1 + dl) cf: dl compensates the mean shrink of the truncating accumulation
@@ -462,91 +616,89 @@ __device__ __forceinline__ void ue_acc8(uint32_t ta_main, uint32_t ta_cross, flo
     for (int i = 0; i < 8; ++i) { const float t = __uint_as_float(a[i]) + __uint_as_float(b[i]); v[i] = fmaf(t, dl, t) * cf; }
 }
 
-// Epilogue of a wide GEMM into the hidden operand (in place): the thread's WQ columns, two passes
-// over tensor memory (row maximum, then scale / split / store).
-//   FWD:  h = relu(acc)   and the ReLU mask of the thread's columns is produced (mask[] out)
+// Epilogue of column block G of a wide GEMM into the hidden operand: the thread's NC8 chunks of 8
+// columns (one pass over tensor memory; the operand scale is known beforehand, see the header).
+//   FWD:  h = relu(acc)   and the ReLU mask bits of these columns are produced (mask[] |=)
 //   !FWD: h = mask ? acc : 0                                           (mask[] in)
-// ta_main / ta_cross: tensor-memory addresses (lane base included) of the thread's first column.
-// 16 consecutive accumulator columns of the thread's lane (no wait).  The thread's first column is a
-// multiple of 8; -DUE_LD16 uses one x16 load (tensor-memory loads need no alignment beyond the
-// 32-bit column: profiles/r02_mb_umma_rates.log "ldalign"), otherwise two x8 loads.
-__device__ __forceinline__ void ue_ld16(uint32_t ta, uint32_t (&v)[16]) {
-#ifdef UE_LD16
-    umma::tmem_ld16(ta, v);
-#else
-    uint32_t a[8], b[8];
-    umma::tmem_ld8(ta, a);
-    umma::tmem_ld8(ta + 8, b);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] = a[i]; v[8 + i] = b[i]; }
-#endif
-}
-
-// NCH = WQ / 16: chunks of 16 hidden columns per thread (compile time: the register arrays below
-// must be statically indexed)
-template <bool FWD, int NCH>
-__device__ __forceinline__ void ue_epi_hidden(const ULayout& L, UCw& c, uint32_t ta_main, uint32_t ta_cross, float cf, float dl,
-                                              uint32_t (&mask)[3], bool bias_col, float& inv_s_out) {
-    // pass 1: row maximum from the hi*hi accumulator alone (the cross terms are ~2^-11 of it; the
-    // scale only has to put the largest element near 2^13, with a factor 4 of headroom below the
-    // f16 maximum), un-scaled: max(relu(v)) = max(0, max v), cf > 0.  The backward form takes the
-    // maximum over ALL of the thread's columns, masked or not: an upper bound is all the scale needs
-    // (a masked-out maximum costs a bit or two of the 2^-39 absolute resolution) and it saves the
-    // per-element mask test.  All loads first, one wait.
-    float m = 0.f, dummy = 0.f;
-    {
-        uint32_t a[NCH][16];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) ue_ld16(ta_main + 16 * j, a[j]);
-        umma::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m = fmaxf(m, FWD ? __uint_as_float(a[j][i]) : fabsf(__uint_as_float(a[j][i])));
-        }
-    }
-    m *= cf;
-    ue_row_max2(L, c, m, dummy);
-    float s, inv_s;
-    ue_scale_of<FWD>(m, s, inv_s);          // forward operands are the biased ones
-    inv_s_out = inv_s;
-    // un-scale, compensate and re-scale with one factor: s and cf are powers of two, (1 + dl) is a
-    // few ulp for these long chains (for the short z-path chain dl is below one ulp and goes through
-    // an FMA instead: ue_acc8 / ue_acc16)
-    const float sc = cf * s * (1.0f + dl);
+// ta_main / ta_cross: tensor-memory addresses (lane base included) of the thread's first column of the
+// block; sc = (un-scale of the accumulators) x (1 + dl) x (scale of the new operand); ssq += sum of
+// squares of the stored (scaled) values.
+template <bool FWD, int NC8, int G>
+__device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uint32_t ta_main, uint32_t ta_cross, float sc,
+                                             uint32_t (&mask)[3], float& ssq) {
     uint8_t* hp = ue_smem + L.s_h;
-    uint32_t nm[3] = {0u, 0u, 0u};
-    // pass 2, software-pipelined over the chunks of 16 columns: the loads of chunk j+1 are in flight
-    // while chunk j is scaled / split / stored (tcgen05.wait::ld waits for everything outstanding, so
-    // the next loads are issued right AFTER the wait)
-    uint32_t a[2][16], b[2][16];
-    ue_ld16(ta_main, a[0]);
-    ue_ld16(ta_cross, b[0]);
+    const int chunk0 = ((2 * G + c.h) * L.WQ) / 8 + c.g * NC8;
+    // software-pipelined over the chunks: the loads of chunk j+1 are in flight while chunk j is scaled /
+    // split / stored (tcgen05.wait::ld waits for everything outstanding, so the next loads are issued
+    // right AFTER the wait)
+#ifdef UE_LOADS_UPFRONT
+    uint32_t a[NC8][8], b[NC8][8];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
+    for (int j = 0; j < NC8; ++j) { umma::tmem_ld8(ta_main + 8 * j, a[j]); umma::tmem_ld8(ta_cross + 8 * j, b[j]); }
+    umma::tmem_ld_wait();
+#define UE_AJ(j) a[j]
+#define UE_BJ(j) b[j]
+#else
+    uint32_t a[2][8], b[2][8];
+    umma::tmem_ld8(ta_main, a[0]);
+    umma::tmem_ld8(ta_cross, b[0]);
+#define UE_AJ(j) a[(j) & 1]
+#define UE_BJ(j) b[(j) & 1]
+#endif
+#pragma unroll
+    for (int j = 0; j < NC8; ++j) {
+#ifndef UE_LOADS_UPFRONT
         umma::tmem_ld_wait();
-        if (j + 1 < NCH) {
-            ue_ld16(ta_main + 16 * (j + 1), a[(j + 1) & 1]);
-            ue_ld16(ta_cross + 16 * (j + 1), b[(j + 1) & 1]);
+        if (j + 1 < NC8) {
+            umma::tmem_ld8(ta_main + 8 * (j + 1), a[(j + 1) & 1]);
+            umma::tmem_ld8(ta_cross + 8 * (j + 1), b[(j + 1) & 1]);
         }
-        const uint32_t mw = FWD ? 0u : mask[j >> 1] >> (16 * (j & 1));
+#endif
+        const int bit0 = (G * NC8 + j) * 8;
+        const uint32_t mw = FWD ? 0u : mask[bit0 >> 5] >> (bit0 & 31);
         uint32_t bits = 0;
-        float lo8[8], hi8[8];
+        float hv[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float v = (__uint_as_float(a[j & 1][i]) + __uint_as_float(b[j & 1][i])) * sc;
-            float hv;
-            if (FWD) { const bool on = v > 0.f; bits |= (on ? 1u : 0u) << i; hv = on ? v : 0.f; }
-            else hv = ((mw >> i) & 1u) ? v : 0.f;
-            if (i < 8) lo8[i] = hv; else hi8[i - 8] = hv;
+        for (int i = 0; i < 8; ++i) {
+            const float v = (__uint_as_float(UE_AJ(j)[i]) + __uint_as_float(UE_BJ(j)[i])) * sc;
+            if (FWD) { const bool on = v > 0.f; bits |= (on ? 1u : 0u) << i; hv[i] = on ? v : 0.f; }
+            else hv[i] = ((mw >> i) & 1u) ? v : 0.f;
+            ssq = fmaf(hv[i], hv[i], ssq);
         }
-        if (FWD) nm[j >> 1] |= bits << (16 * (j & 1));
-        const int chunk = (c.q * L.WQ) / 8 + 2 * j;
-        ue_store_chunk(hp, L.hplane, chunk, c.r, lo8);
-        ue_store_chunk(hp, L.hplane, chunk + 1, c.r, hi8);
+        if (FWD) mask[bit0 >> 5] |= bits << (bit0 & 31);
+        ue_store_chunk(hp, L.hplane, chunk0 + j, c.r, hv);
     }
-    if (FWD) { mask[0] = nm[0]; mask[1] = nm[1]; mask[2] = nm[2]; }
-    if (bias_col && c.q == 0) ue_store_one(hp, L.W / 8, c.r, s);
+#undef UE_AJ
+#undef UE_BJ
+}
+// Both blocks of a wide GEMM, with the barrier protocol around them.  bound_fn(): upper bound of the
+// row maximum of the result (evaluated after the first accumulator wait: it may read the hand-off of
+// the previous epilogue); cf: un-scale of the accumulators (operand scale x weight scale); returns the
+// new operand's inverse scale and (ssq_out) the thread's part of its squared row norm in UNSCALED units.
+// between(blk): work after the wait for block blk (type 0: the v columns behind block c.g).
+template <bool FWD, bool BIASED, int NC8, class FB, class F>
+__device__ __forceinline__ float ue_epi_wide(const ULayout& L, UCw& c, const UType& t, float cf, float dl,
+                                             uint32_t (&mask)[3], float& ssq_out, FB bound_fn, F between) {
+    const uint32_t t0 = c.tmem + c.tl + t.dcol + c.g * (L.WQ / 2);      // the thread's first column of block 0 (main)
+    float ssq = 0.f;
+    if (FWD) { mask[0] = 0u; mask[1] = 0u; mask[2] = 0u; }
+    ue_wait_acc(L, c, 0);
+    ++c.n0;
+    float s, inv_s;
+    ue_scale_of<BIASED>(bound_fn(), s, inv_s);
+    // un-scale, compensate and re-scale with one factor: s and cf are powers of two, (1 + dl) is a
+    // few ulp for these long chains
+    const float sc = cf * s * (1.0f + dl);
+    if (BIASED && c.q == 0) ue_store_one(ue_smem + L.s_h, L.W / 8, c.r, s);
+    between(0);
+    ue_epi_block<FWD, NC8, 0>(L, c, t0, t0 + t.nbh, sc, mask, ssq);
+    ue_operand_ready(L, 0);
+    ue_wait_acc(L, c, 1);
+    ++c.gi;
+    between(1);
+    ue_epi_block<FWD, NC8, 1>(L, c, t0 + 2 * t.nbh, t0 + 3 * t.nbh, sc, mask, ssq);
+    ssq_out = ssq * inv_s * inv_s;
+    return inv_s;
 }
 
 // ReLU-mask scratch: word w of (layer, which, group q) of global row `grow`
@@ -563,13 +715,15 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
                                               float (&zc)[UE_DQ], float (&gs)[UE_DQ]) {
     uint8_t* const zp = ue_smem + L.s_z;
     const float* scal = blob_f + L.o_scal;
-    float inv_s_z, inv_s_h = 1.f;
+    const float sqrt_d = sqrtf((float)L.d);
+    float inv_s_z, inv_s_h = 1.f, zmax;
     // x -> z operand
     {
         float m = 0.f, dummy = 0.f;
 #pragma unroll
         for (int i = 0; i < UE_DQ; ++i) m = fmaxf(m, fabsf(zc[i]));
         ue_row_max2(L, c, m, dummy);
+        zmax = m;
         float s;
         ue_scale_of<true>(m, s, inv_s_z);
         float v[8];
@@ -577,43 +731,50 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
         for (int i = 0; i < 8; ++i) v[i] = zc[i] * s;
         ue_store_chunk(zp, L.zplane, c.q, c.r, v);
         if (c.q == 0) ue_store_one(zp, L.d / 8, c.r, s);
-        ue_operand_ready(L);
+        ue_operand_ready(L, 2);
     }
     float sacc = 0.f;
     const uint32_t tl = c.tmem + c.tl;
     for (int k = L.K - 1; k >= 0; --k) {
+        const float* sk = scal + k * UE_SCAL;
         float vreg[UE_DQ];
         uint32_t mask[3];
-        // ---- G1: [v | h1pre] ---------------------------------------------------------------
+        float ssq;
+        // ---- G1: [v | h1pre];  |h1pre_n| <= ||z||_2 ||W[:,n]||_2 + |b_n|,  ||z||_2 <= sqrt(d) max|z| ----
         {
             const UType& t = L.t[0];
-            const float cf = inv_s_z * __ldg(scal + k * 8 + 0);
-            ue_wait_acc(L, c);
-            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
-            ue_acc8(tm + L.WQ, tx + L.WQ, cf, L.dl[0], vreg);
-            ue_epi_hidden<true, NCH>(L, c, tm, tx, cf, L.dl[1], mask, true, inv_s_h);
+            const float cf = inv_s_z * __ldg(sk + 0);
+            const float bound = fmaf(zmax * sqrt_d, __ldg(sk + 8), __ldg(sk + 12));
+            inv_s_h = ue_epi_wide<true, true, NCH>(L, c, t, cf, L.dl[1], mask, ssq, [&]() { return bound; }, [&](int blk) {
+                if (blk == c.g) {        // the thread's v columns sit behind the hidden columns of block c.g
+                    const uint32_t tv = tl + t.dcol + c.g * 2 * t.nbh + L.WQ;
+                    ue_acc8(tv, tv + t.nbh, cf, L.dl[0], vreg);
+                }
+            });
+            ue_ssq_put(L, c, ssq);
             if (GRAD)
 #pragma unroll
                 for (int w = 0; w < 3; ++w) ue_mask_ptr(mscratch, n_stride, k, 0, c.q, grow)[(size_t)w * n_stride] = mask[w];
-            ue_operand_ready(L);
+            ue_operand_ready(L, 1);
         }
         // ---- G2: h2pre -----------------------------------------------------------------------
         {
             const UType& t = L.t[1];
-            const float cf = inv_s_h * __ldg(scal + k * 8 + 1);
-            ue_wait_acc(L, c);
-            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
-            ue_epi_hidden<true, NCH>(L, c, tm, tx, cf, L.dl[2], mask, true, inv_s_h);
+            const float cf = inv_s_h * __ldg(sk + 1);
+            const float c2 = __ldg(sk + 9), bm = __ldg(sk + 13);
+            inv_s_h = ue_epi_wide<true, true, NCH>(L, c, t, cf, L.dl[2], mask, ssq,
+                                                   [&]() { return fmaf(sqrtf(ue_ssq_get(L, c)), c2, bm); }, [](int) {});
             if (GRAD)
 #pragma unroll
                 for (int w = 0; w < 3; ++w) ue_mask_ptr(mscratch, n_stride, k, 1, c.q, grow)[(size_t)w * n_stride] = mask[w];
-            ue_operand_ready(L);
+            ue_operand_ready(L, 1);
         }
         // ---- G3: [shift | scale] of the thread's transformed columns, coupling inverse -------------
         {
             const UType& t = L.t[2];
-            const float cf = inv_s_h * __ldg(scal + k * 8 + 2);
-            ue_wait_acc(L, c);
+            const float cf = inv_s_h * __ldg(sk + 2);
+            ue_wait_acc(L, c, 1);
+            ++c.gi;
             if (c.g == 1) {
                 float p[16];
                 ue_acc16(tl + t.dcol, tl + t.dcol + t.nbh, cf, L.dl[3], p);
@@ -638,6 +799,7 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
 #pragma unroll
                 for (int i = 0; i < UE_DQ; ++i) m = fmaxf(m, fabsf(zc[i]));
                 ue_row_max2(L, c, m, dummy);
+                zmax = m;
                 float s;
                 ue_scale_of<true>(m, s, inv_s_z);
                 float v[8];
@@ -645,7 +807,7 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
                 for (int i = 0; i < 8; ++i) v[i] = zc[i] * s;
                 ue_store_chunk(zp, L.zplane, c.q, c.r, v);
                 if (c.q == 0) ue_store_one(zp, L.d / 8, c.r, s);
-                ue_operand_ready(L);
+                ue_operand_ready(L, 2);
             }
         }
     }
@@ -661,14 +823,15 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
     }
     ue_row_sum2(L, c, gpart, sacc);
     float logs = 0.f;
-    for (int k = 0; k < L.K; ++k) logs += __ldg(scal + k * 8 + 7);
+    for (int k = 0; k < L.K; ++k) logs += __ldg(scal + k * UE_SCAL + 7);
     const float lq = logs + (-0.5f * (float)L.d * 1.8378770664093453f - (gpart + sacc));
     if (!GRAD) return lq;
     // ---- input-gradient sweep ---------------------------------------------------------------------
     uint8_t* const pp = ue_smem + L.s_par;
     uint8_t* const gp = ue_smem + L.s_gv;
     for (int k = 0; k < L.K; ++k) {
-        float inv_s_par, inv_s_gv;
+        const float* sk = scal + k * UE_SCAL;
+        float inv_s_par, inv_s_gv, pmax;
         // coupling backward: gparam and gv operands
         {
             float gpar[16], gv[UE_DQ];
@@ -694,6 +857,7 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
 #pragma unroll
             for (int i = 0; i < UE_DQ; ++i) mb = fmaxf(mb, fabsf(gv[i]));
             ue_row_max2(L, c, ma, mb);
+            pmax = ma;
             float sa, sb;
             ue_scale_of<false>(ma, sa, inv_s_par);
             ue_scale_of<false>(mb, sb, inv_s_gv);
@@ -710,35 +874,37 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = gv[i] * sb;
             ue_store_chunk(gp, L.pplane, c.q, c.r, v);
-            ue_operand_ready(L);
+            ue_operand_ready(L, 2);
         }
         uint32_t mask[3];
-        // ---- G3T: gh2 = (gparam @ W3) * m2 ---------------------------------------------------
+        float ssq;
+        // ---- G3T: gh2 = (gparam @ W3) * m2;  ||gparam||_2 <= sqrt(d) max|gparam| ------------------
         {
             const UType& t = L.t[3];
-            const float cf = inv_s_par * __ldg(scal + k * 8 + 3);
+            const float cf = inv_s_par * __ldg(sk + 3);
 #pragma unroll
             for (int w = 0; w < 3; ++w) mask[w] = ue_mask_ptr(mscratch, n_stride, k, 1, c.q, grow)[(size_t)w * n_stride];
-            ue_wait_acc(L, c);
-            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
-            ue_epi_hidden<false, NCH>(L, c, tm, tx, cf, L.dl[4], mask, false, inv_s_h);
-            ue_operand_ready(L);
+            const float bound = pmax * sqrt_d * __ldg(sk + 10);
+            inv_s_h = ue_epi_wide<false, false, NCH>(L, c, t, cf, L.dl[4], mask, ssq, [&]() { return bound; }, [](int) {});
+            ue_ssq_put(L, c, ssq);
+            ue_operand_ready(L, 1);
         }
         // ---- G2T: gh1 = (gh2 @ W2) * m1 ------------------------------------------------------
         {
             const UType& t = L.t[4];
-            const float cf = inv_s_h * __ldg(scal + k * 8 + 4);
+            const float cf = inv_s_h * __ldg(sk + 4);
 #pragma unroll
             for (int w = 0; w < 3; ++w) mask[w] = ue_mask_ptr(mscratch, n_stride, k, 0, c.q, grow)[(size_t)w * n_stride];
-            ue_wait_acc(L, c);
-            const uint32_t tm = tl + t.dcol + c.g * t.nbh, tx = tm + 2 * t.nbh;
-            ue_epi_hidden<false, NCH>(L, c, tm, tx, cf, L.dl[5], mask, false, inv_s_h);
-            ue_operand_ready(L);
+            const float c2 = __ldg(sk + 11);
+            inv_s_h = ue_epi_wide<false, false, NCH>(L, c, t, cf, L.dl[5], mask, ssq,
+                                                    [&]() { return sqrtf(ue_ssq_get(L, c)) * c2; }, [](int) {});
+            ue_operand_ready(L, 1);
         }
         // ---- G1T: g = gh1 @ (W1 Wmix1^T) + gv @ Wmix^T ---------------------------------------
         {
-            const float ca = inv_s_h * __ldg(scal + k * 8 + 5), cb = inv_s_gv * __ldg(scal + k * 8 + 6);
-            ue_wait_acc(L, c);
+            const float ca = inv_s_h * __ldg(sk + 5), cb = inv_s_gv * __ldg(sk + 6);
+            ue_wait_acc(L, c, 1);
+            ++c.gi;
             float a[8], b[8];
             const UType& t5 = L.t[5];
             const UType& t6 = L.t[6];
@@ -759,14 +925,14 @@ __device__ __forceinline__ UEnv ue_setup(const ULayout& L) {
     UEnv e;
     e.rank = umma::cluster_ctarank();
     e.warp = threadIdx.x >> 5; e.lane = threadIdx.x & 31;
-    uint32_t* slot = reinterpret_cast<uint32_t*>(ue_smem + L.s_bar + (2 * UE_NSTAGE + 2) * 8);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(ue_smem + L.s_bar + (2 * UE_NSTAGE + 4) * 8);
     // operand buffers start from zero: pad rows, bias chunks and lo planes of the "ones" columns
     for (int i = threadIdx.x; i < L.s_ring / 16; i += UE_THREADS) reinterpret_cast<uint4*>(ue_smem)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         const UBars B = ue_bars(L);
         for (int s = 0; s < UE_NSTAGE; ++s) { umma::mbar_init(B.full + s, e.rank == 0 ? 2 : 1); umma::mbar_init(B.empty + s, 1); }
-        umma::mbar_init(B.dfull, 1);
-        umma::mbar_init(B.aready, 16);
+        umma::mbar_init(B.dfull, 1); umma::mbar_init(B.dfull + 1, 1);
+        umma::mbar_init(B.aready, 16); umma::mbar_init(B.aready + 1, 16);
         umma::mbar_fence_init();
     }
     __syncthreads();
@@ -790,7 +956,7 @@ __device__ __forceinline__ UCw ue_cw(const UEnv& e) {
     const int l = 32 * q4 + e.lane;
     c.r = l & 63; c.h = l >> 6; c.g = e.warp >> 2; c.q = 2 * c.g + c.h;
     c.tl = (uint32_t)(32 * q4) << 16;
-    c.gi = 0; c.xb = 0; c.tmem = e.tmem; c.rank = e.rank;
+    c.gi = 0; c.n0 = 0; c.xb = 0; c.nq = 0; c.tmem = e.tmem; c.rank = e.rank;
     return c;
 }
 
@@ -907,8 +1073,10 @@ k_hmc_step_u(ULayout L, const uint8_t* __restrict__ blob, fab_target_desc tgt, f
                 float zc[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) zc[i] = px[i];
+                UE_T0();
                 plq = ue_flow_eval<true, NCH>(L, c, reinterpret_cast<const float*>(blob), mscratch,
                                          (long long)gridDim.x * UE_ROWS, (long long)blockIdx.x * UE_ROWS + c.r, zc, pgq);
+                UE_ACC(7, blockIdx.x == 0 && threadIdx.x == 0);
                 // many-well target: value and gradient of the thread's columns (pairs stay in one thread)
                 float epart = 0.f;
 #pragma unroll
