@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 INC = os.path.join(ROOT, "include", "fab_b200.h")
 UNITS = {
-    "fab_b200.cu": ["common.cuh", "mma_gemm.cuh", "flow_tile.cuh", "target_tile.cuh", "tile_kernels.cuh",
+    "fab_b200.cu": ["common.cuh", "mma_gemm.cuh", "flow_tile.cuh", "param_grad.cuh", "target_tile.cuh", "tile_kernels.cuh",
                     "misc_kernels.cuh", "buffer_kernels.cuh", "reduce_finish.cuh", "host_util.h", INC],
     "fab_umma.cu": ["common.cuh", "target_tile.cuh", "reduce_finish.cuh", "umma.cuh", "umma_engine.cuh",
                     "host_util.h", INC],

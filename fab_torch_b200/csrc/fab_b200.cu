@@ -8,6 +8,7 @@
 #include <string>
 
 #include "tile_kernels.cuh"
+#include "param_grad.cuh"
 #include "misc_kernels.cuh"
 #include "buffer_kernels.cuh"
 #include "host_util.h"
@@ -183,6 +184,92 @@ int fab_flow_logprob_grad_f32(const fab_flow_desc* flow, const float* d_blob, co
         }
     });
     CK_LAUNCH("k_flow_logprob");
+    return FAB_OK;
+}
+
+/* ---- parameter gradient of sum_i g_i log q(x_i) (param_grad.cuh) --------------------------------- */
+namespace {
+struct PgLayout {            // dense gradient buffer: [K layers][Ga | Gb | Gc | Gd] then [dloc | dlog_scale | sum g]
+    int64_t oa, ob, oc, od, layer_floats, tail_off, total, ws_floats;
+    int splits, rows_per_split;
+};
+PgLayout pg_layout(const fab_flow_desc& f, int64_t n) {
+    PgLayout P{};
+    const int64_t d = f.dim, W = f.width, p2 = 2 * f.d2;
+    P.oa = 0; P.ob = P.oa + (d + 1) * W; P.oc = P.ob + d * d; P.od = P.oc + W * (W + 1);
+    P.layer_floats = P.od + p2 * (W + 1);
+    P.tail_off = P.layer_floats * f.n_layers;
+    P.total = P.tail_off + 2 * d + 1;
+    P.rows_per_split = 256;
+    P.splits = (int)std::max<int64_t>(1, (n + P.rows_per_split - 1) / P.rows_per_split);
+    const int64_t mx = std::max<int64_t>({(d + 1) * W, d * d, W * (W + 1), p2 * (W + 1)});
+    P.ws_floats = mx * P.splits * std::max(1, f.n_layers);
+    return P;
+}
+}  // namespace
+
+/* offs[20]: [0] tape floats, [1] tape row stride, [2..8] offsets of z_in, h1, h2, gparam, gh2, gh1, gv
+ * in a row, [9] float offset of the final latent block, [10] gradient floats, [11] floats per layer,
+ * [12..15] offsets of Ga, Gb, Gc, Gd in a layer, [16] offset of the tail, [17] workspace floats. */
+int fab_flow_param_grad_layout(const fab_flow_desc* flow, int64_t n, int64_t* offs) {
+    if (!flow_ok(flow) || n < 0 || !offs) return fail(FAB_E_INVALID, "fab_flow_param_grad_layout: bad arguments");
+    const FabTape t = make_tape(*flow, nullptr, n);
+    const PgLayout P = pg_layout(*flow, n);
+    offs[0] = (int64_t)flow->n_layers * n * t.RS + n * fab_round4(flow->dim);
+    offs[1] = t.RS; offs[2] = t.o_z; offs[3] = t.o_h1; offs[4] = t.o_h2; offs[5] = t.o_gpar;
+    offs[6] = t.o_gh2; offs[7] = t.o_gh1; offs[8] = t.o_gv;
+    offs[9] = (int64_t)flow->n_layers * n * t.RS;
+    offs[10] = P.total; offs[11] = P.layer_floats; offs[12] = P.oa; offs[13] = P.ob; offs[14] = P.oc; offs[15] = P.od;
+    offs[16] = P.tail_off; offs[17] = P.ws_floats;
+    return FAB_OK;
+}
+
+int fab_flow_logprob_tape_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_x,
+                              float* d_log_q, float* d_grad, float* d_tape, int64_t n, void* stream) {
+    if (!flow_ok(flow) || !d_blob || !d_x || !d_log_q || !d_tape || n < 0)
+        return fail(FAB_E_INVALID, "fab_flow_logprob_tape_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    TileLayout L;
+    const int T = pick_tile(*flow, n, true, sample_state, &L);
+    if (T == 0) return fail(FAB_E_INVALID, "no tile variant fits shared memory for this flow");
+    const unsigned grid = (unsigned)((n + T - 1) / T);
+    const size_t sm = (size_t)L.total_floats * 4;
+    const FabTape tape = make_tape(*flow, d_tape, n);
+    DISPATCH_TP(L, {
+        if (int e = set_smem(k_flow_tape<TT>, L)) return e;
+        k_flow_tape<TT><<<grid, FAB_NT, sm, (cudaStream_t)stream>>>(L, *flow, d_blob, d_x, d_log_q, d_grad, tape,
+                                                                    (long long)n);
+    });
+    CK_LAUNCH("k_flow_tape");
+    return FAB_OK;
+}
+
+int fab_flow_param_grad_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_tape,
+                            const float* d_g, int64_t n, float* d_out, float* d_workspace, void* stream) {
+    if (!flow_ok(flow) || !d_blob || !d_tape || !d_g || !d_out || !d_workspace || n < 1)
+        return fail(FAB_E_INVALID, "fab_flow_param_grad_f32: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const FabTape tape = make_tape(*flow, const_cast<float*>(d_tape), n);
+    const PgLayout P = pg_layout(*flow, n);
+    const int d = flow->dim, W = flow->width, p2 = 2 * flow->d2, K = flow->n_layers;
+    auto gemm = [&](int offA, int M, int offB, int N, int64_t out_off) -> int {
+        const dim3 grid((unsigned)(((M + WG_BM - 1) / WG_BM) * ((N + WG_BN - 1) / WG_BN)), (unsigned)P.splits, (unsigned)K);
+        k_wgrad<<<grid, 256, 0, s>>>(tape, offA, M, offB, N, d_g, P.rows_per_split, d_workspace);
+        CK_LAUNCH("k_wgrad");
+        const dim3 rg((unsigned)std::min<int64_t>(((int64_t)M * N + 255) / 256, 1024), (unsigned)K);
+        k_wgrad_reduce<<<rg, 256, 0, s>>>(d_workspace, P.splits, M * N, d_out, P.layer_floats, out_off);
+        CK_LAUNCH("k_wgrad_reduce");
+        return FAB_OK;
+    };
+    if (K > 0) {
+        if (int e = gemm(tape.o_z, d + 1, tape.o_gh1, W, P.oa)) return e;
+        if (int e = gemm(tape.o_z, d, tape.o_gv, d, P.ob)) return e;
+        if (int e = gemm(tape.o_gh2, W, tape.o_h1, W + 1, P.oc)) return e;
+        if (int e = gemm(tape.o_gpar, p2, tape.o_h2, W + 1, P.od)) return e;
+    }
+    k_base_grad<<<d + 1, 256, 0, s>>>(tape.layer(K), fab_round4(d), d, d_blob + flow->off_base_loc,
+                                      d_blob + flow->off_base_log_scale, d_g, (long long)n, d_out + P.tail_off);
+    CK_LAUNCH("k_base_grad");
     return FAB_OK;
 }
 

@@ -180,12 +180,46 @@ __device__ __noinline__ float slot_column_sum(const float* scl, int nj, int& p) 
     return s;
 }
 
+// ---- activation tape for the parameter gradient (param_grad.cuh) -------------
+// With TAPE the evaluation writes, per coupling layer and particle, one row
+//   [z_in (d) | 1 | h1 (W) | 1 | h2 (W) | 1 | gparam (2 d2) | gh2 (W) | gh1 (W) | gv (d)]      (segments padded to 4 floats)
+// to global memory: the operands of the weight-gradient GEMMs (batch = the contraction dimension;
+// the ones columns turn the bias gradients into GEMM rows / columns).  Layer k's rows start at
+// base + k n RS, the final latent z_K at base + K n RS with row stride DP.
+struct FabTape {
+    float* base;
+    long long n;
+    int RS, o_z, o_h1, o_h2, o_gpar, o_gh2, o_gh1, o_gv;
+    __host__ __device__ float* layer(int k) const { return base + (size_t)k * n * RS; }
+};
+__host__ inline FabTape make_tape(const fab_flow_desc& f, float* base, long long n) {
+    FabTape t{};
+    t.base = base; t.n = n;
+    int o = 0;
+    auto take = [&](int c) { int r = o; o += fab_round4(c); return r; };
+    t.o_z = take(f.dim + 1); t.o_h1 = take(f.width + 1); t.o_h2 = take(f.width + 1);
+    t.o_gpar = take(2 * f.d2); t.o_gh2 = take(f.width); t.o_gh1 = take(f.width); t.o_gv = take(f.dim);
+    t.RS = o;
+    return t;
+}
+// operand buffer (k-major, slot stride S) -> rows of the tape; with ONE a trailing 1 per row
+template <int TP, bool ONE>
+__device__ __forceinline__ void tape_dump(float* dst, int RS, const float* src, int nfeat, int np) {
+    constexpr int S = ActL<TP>::S;
+    const int nf1 = nfeat + (ONE ? 1 : 0);
+    for (int e = threadIdx.x; e < nf1 * np; e += FAB_NT) {
+        const int p = e / nf1, j = e - p * nf1;
+        dst[(size_t)p * RS + j] = (ONE && j == nfeat) ? 1.0f : src[(size_t)j * S + p];
+    }
+}
+
 // x in zsel(L, cur) -> z in zsel(L, cur') (cur' returned), log q in lq_out[p] (shared, p < TP).  With
 // SAVE the per-layer (y2, exp(-scale), ReLU masks) needed by flow_backward are kept and b.gs is
 // set to d log N(z) / dz.
-template <int TP, bool SAVE>
+template <int TP, bool SAVE, bool TAPE = false>
 __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
-                            const float* __restrict__ blob, int cur, float* lq_out) {
+                            const float* __restrict__ blob, int cur, float* lq_out,
+                            FabTape tape = FabTape{}, long long row0 = 0, int np = 0) {
     const TileBufs b = tile_bufs(L);
     constexpr int S = ActL<TP>::S;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -215,6 +249,12 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
         prof_mark(3);
         const int KSe = mlp_tail<TP, SAVE>(L, lay, f, k,
                                            k > 0 ? lay - f.layer_stride + f.o_mw1 : nullptr, NT1, false, L.D16 / 16);
+        if (TAPE) {      // operands of dM1 / dWmix (z_in), dW2 (h1), dW3 (h2); all three stay valid until here
+            float* row = tape.layer(k) + (size_t)row0 * tape.RS;
+            tape_dump<TP, true>(row + tape.o_z, tape.RS, zsel(L, cur), L.d, np);
+            tape_dump<TP, true>(row + tape.o_h1, tape.RS, b.h1, f.width, np);
+            tape_dump<TP, true>(row + tape.o_h2, tape.RS, b.h2, f.width, np);
+        }
         // coupling inverse: y2 = (v2 - shift) * exp(-scale)
         {
             const float* b3 = lay + f.o_b3;
@@ -240,6 +280,14 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
     // base Gaussian: log N(z; loc, exp(log_scale)) and its z-gradient
     {
         const float* z = zsel(L, cur);
+        if (TAPE) {
+            constexpr int S_ = ActL<TP>::S;
+            float* zf = tape.layer(L.K) + (size_t)row0 * L.DP;
+            for (int e = threadIdx.x; e < L.d * np; e += FAB_NT) {
+                const int p = e / L.d, j = e - p * L.d;
+                zf[(size_t)p * L.DP + j] = z[(size_t)j * S_ + p];
+            }
+        }
         for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
             const int j = e / TP, p = e - j * TP;
             const float inv = b.inv[j];
@@ -261,9 +309,10 @@ __device__ int flow_inverse(const TileLayout& L, const fab_flow_desc& f,
 }
 
 // b.gs holds d log q / d z on entry (set by flow_inverse<SAVE=true>) and d log q / d x on exit.
-template <int TP>
+template <int TP, bool TAPE = false>
 __device__ void flow_backward(const TileLayout& L, const fab_flow_desc& f,
-                              const float* __restrict__ blob) {
+                              const float* __restrict__ blob,
+                              FabTape tape = FabTape{}, long long row0 = 0, int np = 0) {
     const TileBufs b = tile_bufs(L);
     constexpr int S = ActL<TP>::S;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -314,6 +363,13 @@ __device__ void flow_backward(const TileLayout& L, const fab_flow_desc& f,
         PF_L(mma_prefetch(reinterpret_cast<const float4*>(lay + f.o_w1mt), L.D8 / 8, true, (L.W16 + L.D16) / 16);)
         __syncthreads();
         prof_mark(13);
+        if (TAPE) {      // unit-seed gradients of this layer: gparam, gh2, gh1, gv (all still in place)
+            float* row = tape.layer(k) + (size_t)row0 * tape.RS;
+            tape_dump<TP, false>(row + tape.o_gpar, tape.RS, b.par, 2 * L.d2, np);
+            tape_dump<TP, false>(row + tape.o_gh2, tape.RS, b.h2, f.width, np);
+            tape_dump<TP, false>(row + tape.o_gh1, tape.RS, b.h1, f.width, np);
+            tape_dump<TP, false>(row + tape.o_gv, tape.RS, gv, L.d, np);
+        }
         PF_E(if (k + 1 < L.K)
             mma_prefetch(reinterpret_cast<const float4*>(lay + f.layer_stride + f.o_w3t), L.NTH, false, L.P16 / 16);)
         // g_u = [gh1 | gv] @ [W1 Wmix[:, :d1]^T ; Wmix^T]

@@ -11,9 +11,13 @@ in the same order as normflows (so `torch.manual_seed(s)` gives the same weights
 
 Hot path: `sample_and_log_prob`, `log_prob` and d log_prob / dx run as CUDA kernels on a packed
 weight blob (layout: include/fab_b200.h) that is rebuilt lazily whenever a parameter changes.
-Gradients w.r.t. the flow parameters (needed only by the training loss, fab/core.py:112-118 --
-SURVEY §8f row 2, outside the sampler) are produced by re-evaluating the same maths with torch
-ops on the GPU inside `backward`.
+Gradients of `log_prob` w.r.t. the flow parameters (the training loss, fab/core.py:112-118 -- SURVEY
+§8f row 2) are CUDA kernels too: the forward pass of `log_prob` records an activation tape
+(`fab_flow_logprob_tape_f32`) whenever a parameter requires grad, and `backward` turns it into the
+weight gradients with batch-contraction GEMMs (`fab_flow_param_grad_f32`, csrc/param_grad.cuh); what
+is left for torch is the chain rule through the merged / LU-parameterised matrices in PARAMETER
+space ([W x d]-sized).  `sample_and_log_prob` (not on the FAB-loss path: the AIS points are detached,
+fab/core.py:120-128) still differentiates w.r.t. parameters by re-running the torch-op restatement.
 """
 import math
 from typing import Tuple
@@ -202,6 +206,18 @@ class B200RealNVP(TrainableDistribution):
         W_inv = U_inv @ L_inv @ P.transpose(1, 2)
         return W, W_inv, log_S.sum(dim=1)
 
+    def _mixing_W(self):
+        """W [K,d,d] and sum(log_S) [K] only (differentiable w.r.t. L, U, log_S)."""
+        mixes = [self._nf_model.flows[2 * k + 1] for k in range(self.n_flow_layers)]
+        P = torch.stack([m.P for m in mixes])
+        eye = mixes[0].eye
+        L = torch.tril(torch.stack([m.L for m in mixes]), diagonal=-1) + eye
+        log_S = torch.stack([m.log_S for m in mixes])
+        sign_S = torch.stack([m.sign_S for m in mixes])
+        U = torch.triu(torch.stack([m.U for m in mixes]), diagonal=1) + \
+            torch.diag_embed(sign_S * torch.exp(log_S))
+        return P @ L @ U, log_S.sum(dim=1)
+
     def _pack(self) -> torch.Tensor:
         d = self.desc()
         dev = self._nf_model.q0.loc.device
@@ -387,6 +403,78 @@ class B200RealNVP(TrainableDistribution):
         _lib.check(rc, "fab_flow_logprob_grad_f32")
         return log_q, grad
 
+    # ---- parameter gradient (csrc/param_grad.cuh) ------------------------------------------------
+    def _pg_layout(self, n: int):
+        import ctypes as C
+        offs = (C.c_int64 * 20)()
+        _lib.check(_lib.lib().fab_flow_param_grad_layout(self.desc(), n, offs), "fab_flow_param_grad_layout")
+        return [int(v) for v in offs]
+
+    def cuda_log_prob_tape(self, x: torch.Tensor, with_grad: bool):
+        """log q, (optionally) d log q / dx and the activation tape of the parameter gradient."""
+        x = _lib.f32(x).contiguous()
+        n = x.shape[0]
+        offs = self._pg_layout(n)
+        log_q = torch.empty(n, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if with_grad else None
+        tape = torch.empty(max(offs[0], 1), dtype=torch.float32, device=x.device)
+        rc = _lib.lib().fab_flow_logprob_tape_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(x),
+                                                  _lib.ptr(log_q), _lib.ptr(grad), _lib.ptr(tape), n,
+                                                  _lib.stream_ptr(x.device))
+        _lib.check(rc, "fab_flow_logprob_tape_f32")
+        return log_q, grad, tape
+
+    def cuda_param_grad(self, tape: torch.Tensor, g: torch.Tensor):
+        """Gradients of sum_i g_i log q(x_i) for every parameter, in `self.parameters()` order."""
+        n = g.shape[0]
+        offs = self._pg_layout(n)
+        total, LS, oa, ob, oc, od, tail_off, ws = offs[10], offs[11], offs[12], offs[13], offs[14], offs[15], offs[16], offs[17]
+        dev = tape.device
+        out = torch.empty(total, dtype=torch.float32, device=dev)
+        wsb = torch.empty(max(ws, 1), dtype=torch.float32, device=dev)
+        g = _lib.f32(g).contiguous()
+        rc = _lib.lib().fab_flow_param_grad_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(tape), _lib.ptr(g), n,
+                                                _lib.ptr(out), _lib.ptr(wsb), _lib.stream_ptr(dev))
+        _lib.check(rc, "fab_flow_param_grad_f32")
+        K, d, W = self.n_flow_layers, self.dim, self.width
+        dsc = self.desc()
+        d1, p2 = dsc.d1, 2 * dsc.d2
+        q0 = self._nf_model.q0
+        grads = {id(q0.loc): out[tail_off:tail_off + d].view(1, d),
+                 id(q0.log_scale): out[tail_off + d:tail_off + 2 * d].view(1, d)}
+        if K:
+            lay = out[:K * LS].view(K, LS)
+            Ga = lay[:, oa:oa + (d + 1) * W].view(K, d + 1, W)
+            Gb = lay[:, ob:ob + d * d].view(K, d, d)
+            Gc = lay[:, oc:oc + W * (W + 1)].view(K, W, W + 1)
+            Gd = lay[:, od:od + p2 * (W + 1)].view(K, p2, W + 1)
+            blocks = [self._nf_model.flows[2 * k] for k in range(K)]
+            mixes = [self._nf_model.flows[2 * k + 1] for k in range(K)]
+            with torch.enable_grad():
+                Wm, logs = self._mixing_W()
+            W1 = torch.stack([b.linears[0].weight.detach() for b in blocks])          # [K, W, d1]
+            dM1 = Ga[:, :d, :]                                                          # [K, d, W]
+            dW1 = dM1.transpose(1, 2) @ Wm.detach()[:, :, :d1]                          # [K, W, d1]
+            dWm = Gb.clone()
+            dWm[:, :, :d1] += dM1 @ W1
+            perm = torch.cat([torch.arange(0, p2, 2), torch.arange(1, p2, 2)]).to(dev)
+            dW3 = torch.empty(K, p2, W, dtype=torch.float32, device=dev)
+            db3 = torch.empty(K, p2, dtype=torch.float32, device=dev)
+            dW3[:, perm, :] = Gd[:, :, :W]
+            db3[:, perm] = Gd[:, :, W]
+            mix_params = [p for m in mixes for p in (m.L, m.log_S, m.U)]
+            sum_g = out[tail_off + 2 * d]
+            with torch.enable_grad():
+                mg = torch.autograd.grad([Wm, logs], mix_params, grad_outputs=[dWm, sum_g.expand(K)])
+            for k in range(K):
+                l1, l2, l3 = blocks[k].linears
+                grads[id(l1.weight)] = dW1[k]; grads[id(l1.bias)] = Ga[k, d, :]
+                grads[id(l2.weight)] = Gc[k, :, :W]; grads[id(l2.bias)] = Gc[k, :, W]
+                grads[id(l3.weight)] = dW3[k]; grads[id(l3.bias)] = db3[k]
+            for p, gr in zip(mix_params, mg):
+                grads[id(p)] = gr
+        return [grads[id(p)] for p in self.parameters()]
+
     # ---- the same maths in torch ops (GPU), differentiable w.r.t. parameters -----------------
     def _coupling_params(self, k, v1):
         l1, l2, l3 = self._nf_model.flows[2 * k].linears
@@ -428,33 +516,36 @@ class B200RealNVP(TrainableDistribution):
 
 
 class _LogProbFn(torch.autograd.Function):
-    """forward: CUDA value + input-gradient; backward: dx from the saved input-gradient, dtheta (only
-    if some parameter requires grad) by re-running the torch-op restatement."""
+    """forward: CUDA value (+ input-gradient, + activation tape when a parameter requires grad);
+    backward: dx from the saved input-gradient, dtheta from the tape (fab_flow_param_grad_f32)."""
 
     @staticmethod
     def forward(ctx, flow: B200RealNVP, x, *params):
         need_dx = x.requires_grad
-        log_q, grad = flow.cuda_log_prob(x.detach(), with_grad=need_dx)
+        need_dp = any(ctx.needs_input_grad[2:])
+        tape = None
+        if need_dp and x.shape[0] > 0:
+            log_q, grad, tape = flow.cuda_log_prob_tape(x.detach(), with_grad=need_dx)
+        else:
+            log_q, grad = flow.cuda_log_prob(x.detach(), with_grad=need_dx)
         ctx.flow = flow
         ctx.n_params = len(params)
-        ctx.save_for_backward(x.detach(), grad if grad is not None else x.new_empty(0))
+        ctx.save_for_backward(grad if grad is not None else x.new_empty(0),
+                              tape if tape is not None else x.new_empty(0))
         ctx.has_dx = need_dx
+        ctx.has_tape = tape is not None
         return log_q
 
     @staticmethod
     def backward(ctx, g):
-        x, grad = ctx.saved_tensors
+        grad, tape = ctx.saved_tensors
         flow = ctx.flow
         dx = g[:, None] * grad if (ctx.has_dx and ctx.needs_input_grad[1]) else None
         dparams = [None] * ctx.n_params
-        if any(ctx.needs_input_grad[2:]):
-            with torch.enable_grad():
-                params = [p for p in flow.parameters()]
-                wanted = [p for p, need in zip(params, ctx.needs_input_grad[2:]) if need]
-                lq = flow.torch_log_prob(x)
-                gs = torch.autograd.grad(lq, wanted, grad_outputs=g, allow_unused=True)
-            it = iter(gs)
-            dparams = [next(it) if need else None for need in ctx.needs_input_grad[2:]]
+        if any(ctx.needs_input_grad[2:]) and ctx.has_tape:
+            with torch.no_grad():
+                gs = flow.cuda_param_grad(tape, g)
+            dparams = [gr if need else None for gr, need in zip(gs, ctx.needs_input_grad[2:])]
         return (None, dx, *dparams)
 
 

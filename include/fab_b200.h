@@ -292,6 +292,31 @@ int fab_buffer_adjust_f32(float* d_buf_log_w, float* d_buf_log_q, const int64_t*
                           void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Parameter gradient of  sum_i g_i log q_theta(x_i)  -- the theta-gradient of the FAB loss
+ * (fab/core.py:112-118: loss = -mean(softmax(log_w) * log q(x)); minibatch loop
+ * fab/train_with_prioritised_buffer.py:158-186), replacing loss.backward() through
+ * fab/wrappers/normflows.py:20-24.
+ *   fab_flow_logprob_tape_f32: log q, optionally d log q / dx, and the activation tape (per layer
+ *     and particle: z_in | 1 | h1 | 1 | h2 | 1 | gparam | gh2 | gh1 | gv, see csrc/flow_tile.cuh).
+ *   fab_flow_param_grad_f32: weight gradients as batch-contraction GEMMs over the tape, written as
+ *     dense blocks per layer
+ *         Ga [(d+1) x W]   rows 0..d-1: dM1 = d/d(Wmix[:, :d1] W1^T), row d: d/d b1
+ *         Gb [d x d]       direct part of d/d Wmix   (full: Gb + [dM1 W1 | 0])
+ *         Gc [W x (W+1)]   d/d W2 ([out][in]) | d/d b2
+ *         Gd [2 d2 x (W+1)] d/d W3 (rows: the d2 shifts, then the d2 scales) | d/d b3
+ *     then [d/d loc (d) | d/d log_scale (d) | sum_i g_i (= d/d sum(log_S) of every layer)].
+ *     d/d W1 = dM1^T Wmix[:, :d1] and the LU parameters of Wmix follow in parameter space (host).
+ * Deterministic (fixed batch slices, added in order).  fab_flow_param_grad_layout reports all sizes.
+ * ------------------------------------------------------------------------------------- */
+int fab_flow_param_grad_layout(const fab_flow_desc* flow, int64_t n, int64_t* offs /* [20] */);
+int fab_flow_logprob_tape_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_x,
+                              float* d_log_q, float* d_grad /* may be NULL */, float* d_tape,
+                              int64_t n, void* stream);
+int fab_flow_param_grad_f32(const fab_flow_desc* flow, const float* d_blob, const float* d_tape,
+                            const float* d_g, int64_t n, float* d_out, float* d_workspace,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Row-tile engine: the same flow evaluation (fab/wrappers/normflows.py:20-24 log_prob, its input
  * gradient as used by fab/sampling_methods/base.py:50-56) and the same fused HMC outer step
  * (transition_operators/hmc.py:129-160) on the 5th-generation tensor cores: tcgen05.mma with

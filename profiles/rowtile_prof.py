@@ -12,7 +12,7 @@ os.environ["FAB_ENGINE"] = "rowtile"
 import bench
 from fab_torch_b200 import _lib
 
-NAMES = ["cw wait acc", "cw epilogue", "mma wait aready", "mma wait stages", "mma issue", "prod wait slot",
+NAMES = ["cw wait D0", "cw wait D1", "mma wait A0/A1", "mma wait stages", "mma issue", "prod wait slot",
          "cw barrier", "cw flow evals", "wait G1", "wait G2", "wait G3", "wait G3T", "wait G2T", "wait G1T"]
 
 
