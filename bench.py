@@ -284,7 +284,7 @@ def build_gpu(cfg, device, group):
                                   epsilon=cfg["epsilon"], n_outer=cfg["n_outer"], L=cfg["L"]).to(device)
     ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=cfg["p_target"],
                                        alpha=cfg["alpha"], n_intermediate_distributions=cfg["M"],
-                                       process_group=group, use_cuda_graph=group is None)
+                                       process_group=group, use_cuda_graph=True)
     return flow, target, op, ais
 
 
@@ -432,7 +432,7 @@ def run_gpu_arm(args):
                     config=config_block(cfg, world),
                     engine=dict(hmc_step="row-tile tcgen05 (f16 hi/lo operands, fp32 accumulate)" if rowtile
                                 else "warp-level mma.sync 3xTF32 (weights rounded to 22 bits)",
-                                cuda_graph=bool(ais.use_cuda_graph and world == 1)),
+                                cuda_graph=bool(ais.use_cuda_graph)),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d * world,
                              d2h_bytes_per_step=d2h * world, ms_per_step=total_e2e_ms / args.steps),
                     gpu_launches=launches_per_step * args.steps, clocks=clock_rec, roofline=roof,
@@ -455,7 +455,17 @@ def run_gpu_arm(args):
             line["parity"] = parity_leg(cfg, B_local, device)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs hold NCCL kernels: release them before the communicator goes away
+        ais.release_graphs()
+        torch.cuda.synchronize()
+        dist.barrier()
+        # (belt and braces: a teardown that does not return must not hold the GPU box)
+        import threading
+        guard = threading.Timer(30.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def multi_gpu_parity(ais, B_global, device, group, rank, world):

@@ -179,7 +179,21 @@ class AnnealedImportanceSampler:
         self._filter(pt, log_w, counts[0:1], counts[1:2])          # "chain end"
         if logging:
             self._ess(log_w, None, counts[1:2], rec[3:6])
+        if self._world()[0] > 1:
+            # whole-batch live counts (the reference decides "no valid points" on the whole batch,
+            # ais.py:202-204): summed on the device inside the chain, read back with the record
+            import torch.distributed as dist
+            gcounts = counts.to(torch.float32)
+            dist.all_reduce(gcounts, group=self.process_group)
+            rec[6:8] = gcounts
         return pt, log_w, counts, rec
+
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (and their persistent buffers).  With a process group, call
+        this before `destroy_process_group`: the graphs hold the communicator's kernels."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        self._graph_warm.clear()
 
     def set_next_noise(self, eps: torch.Tensor, noise_a: torch.Tensor, noise_b: torch.Tensor):
         """Pre-drawn randomness for the NEXT `sample_and_log_weights` call, e.g. pinned host
@@ -202,7 +216,7 @@ class AnnealedImportanceSampler:
         hyper = tuple(getattr(op, k, None) for k in ("L", "n_outer", "max_grad", "target_p_accept",
                                                      "n_updates", "target_prob_accept"))
         ukey = flow.umma_blob().data_ptr() if flow.use_rowtile(local) else 0
-        key = (local, logging, self.p_target, self.alpha, op.p_target, op.alpha,
+        key = (local, self._world()[0], logging, self.p_target, self.alpha, op.p_target, op.alpha,
                bool(getattr(op, "eval_mode", False)), getattr(op, "adjust_step_size", None),
                blob.data_ptr(), ukey, id(op), str(dev), state_ptrs, tkey, hyper,
                _lib.engine_choice())
@@ -263,7 +277,9 @@ class AnnealedImportanceSampler:
         op = self.transition_operator
         op.process_group = self.process_group
         local = fdist.shard_size(batch_size, self.process_group)
-        if self.use_cuda_graph and self.process_group is None:
+        if self.use_cuda_graph:
+            # (with a process group the tuner / ESS collectives are captured with the kernels: NCCL
+            # supports stream capture; every rank captures and replays the same sequence)
             pt, log_w, counts, rec = self._run_graphed(local, logging)
         else:
             if self._next_noise is not None:
@@ -287,10 +303,7 @@ class AnnealedImportanceSampler:
         if world > 1:
             # the reference decides on the WHOLE batch (ais.py:202-204); deciding per shard would let
             # one rank raise while the others wait in the next collective
-            import torch.distributed as dist
-            tot = torch.tensor([n_init, n_end], dtype=torch.int64, device=dev)
-            dist.all_reduce(tot, group=self.process_group)
-            g_init, g_end = int(tot[0]), int(tot[1])
+            g_init, g_end = int(h[2 + 6]), int(h[2 + 7])
         if g_init == 0:
             raise Exception("No valid points generated in sampling the chain init")
         if g_end == 0:
