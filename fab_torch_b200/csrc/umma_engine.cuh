@@ -38,9 +38,14 @@
 //     columns the accumulators do not use; ReLU masks (80 bits per thread and GEMM) in a caller-
 //     owned scratch buffer (L2 resident).
 //
-// Warp roles (320 threads): warps 0-7 compute (epilogues, coupling, leapfrog, accept), warp 8
-// lane 0 issues the MMAs (leader CTA) or relays "my half of the weights has landed" to the leader
-// (peer CTA), warp 9 lane 0 streams weight stages global -> shared with cp.async.bulk.
+// Warp roles (352 threads): warps 0-7 compute (epilogues, coupling, leapfrog, accept); warps 8 and
+// 10 of the leader CTA issue the MMAs -- TWO issuers, because one thread issues at most one
+// tcgen05.mma per ~45 cycles plus its address arithmetic (~73 cycles per MMA measured) while these
+// small MMAs (M 128 x N 160 x K 16 per pair) execute in ~45: warp 8 issues the hi*hi product of the
+// wide GEMMs and the narrow GEMMs, warp 10 the two cross products (their own accumulator, so the two
+// instruction streams never order against each other); both run the same issue program and commit
+// every barrier.  Warp 8 of the peer CTA relays "my half of the weights has landed" to the leader;
+// warp 9 lane 0 streams weight stages global -> shared with cp.async.bulk.
 #pragma once
 #include <cuda_fp16.h>
 #include "umma.cuh"
@@ -48,7 +53,7 @@
 #include "target_tile.cuh"
 
 #define UE_ROWS 64
-#define UE_THREADS 320
+#define UE_THREADS 352
 #define UE_CTHREADS 256
 #define UE_STAGE_BYTES 22528      // two k-steps of the widest operand (352 rows x 32 bytes each)
 #define UE_NSTAGE 4
@@ -417,6 +422,7 @@ __device__ void ue_relay(const ULayout& L, int n_evals, bool grad) {
 // every instruction between two tcgen05.mma counts (the unrolled control flow of an earlier version
 // was 16 k SASS lines and stalled on instruction fetch).  Every lane executes the loop, the MMAs and
 // commits are predicated on one elected lane, so descriptors and addresses stay in uniform registers.
+template <int ROLE>
 __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) {
     const UBars B = ue_bars(L);
     const uint32_t sbase4 = umma::smem_u32(ue_smem) >> 4, ring4 = (umma::smem_u32(ue_smem) + L.s_ring) >> 4;
@@ -435,6 +441,8 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
                 UE_T0(); umma::mbar_wait_cluster(B.aready + 1, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
             }
             if (f & UOP_NEWSTAGE) {
+                // (a helper warp that watches the stage barriers and publishes a counter for the issuers was
+                // measured: no gain once there are two issuers, 0.7811 vs 0.7813 ms per launch)
                 const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
                 UE_T0(); umma::mbar_wait_cluster(B.full + slot, par); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
                 sb4 = ring4 + slot * (UE_STAGE_BYTES >> 4);
@@ -445,13 +453,19 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
                 uint32_t ah = sbase4 + o.a, bk = sb4 + o.b, acc = (f & UOP_ACC) ? 1u : 0u;
                 const uint32_t al = o.a_lo, kstr = o.kstr, d0 = tmem + o.d0, d1 = tmem + o.d1, id0 = o.idesc0, id1 = o.idesc1, nbh = o.nbh;
                 if (f & UOP_WIDE) {
-                    for (uint32_t n = o.count; n > 0; --n) {
-                        umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id0, acc, lead);           // cross  = lo * hi
-                        umma::mma_ss2_pred(d1, desc(ah), desc(bk + nbh), id0, 1u, lead);           // cross += hi * lo
-                        umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // main   = hi * hi
-                        ah += 128; bk += kstr; acc = 1u;
+                    if (ROLE == 0) {
+                        for (uint32_t n = o.count; n > 0; --n) {
+                            umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // main   = hi * hi
+                            ah += 128; bk += kstr; acc = 1u;
+                        }
+                    } else {
+                        for (uint32_t n = o.count; n > 0; --n) {
+                            umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id0, acc, lead);           // cross  = lo * hi
+                            umma::mma_ss2_pred(d1, desc(ah), desc(bk + nbh), id0, 1u, lead);           // cross += hi * lo
+                            ah += 128; bk += kstr; acc = 1u;
+                        }
                     }
-                } else {
+                } else if (ROLE == 0) {
                     for (uint32_t n = o.count; n > 0; --n) {
                         umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // [hi*hi | hi*lo]
                         umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id1, 1u, lead);            // += lo*hi
@@ -930,8 +944,8 @@ __device__ __forceinline__ UEnv ue_setup(const ULayout& L) {
     for (int i = threadIdx.x; i < L.s_ring / 16; i += UE_THREADS) reinterpret_cast<uint4*>(ue_smem)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         const UBars B = ue_bars(L);
-        for (int s = 0; s < UE_NSTAGE; ++s) { umma::mbar_init(B.full + s, e.rank == 0 ? 2 : 1); umma::mbar_init(B.empty + s, 1); }
-        umma::mbar_init(B.dfull, 1); umma::mbar_init(B.dfull + 1, 1);
+        for (int s = 0; s < UE_NSTAGE; ++s) { umma::mbar_init(B.full + s, e.rank == 0 ? 2 : 1); umma::mbar_init(B.empty + s, 2); }
+        umma::mbar_init(B.dfull, 2); umma::mbar_init(B.dfull + 1, 2);      // one commit per issuer
         umma::mbar_init(B.aready, 16); umma::mbar_init(B.aready + 1, 16);
         umma::mbar_fence_init();
     }
@@ -996,9 +1010,11 @@ k_flow_logprob_u(ULayout L, const uint8_t* __restrict__ blob, const float* __res
             }
         }
     } else if (e.warp == 8) {
-        if (e.rank == 0) ue_mma(L, e.tmem, 1, GRAD); else ue_relay(L, 1, GRAD);
-    } else {
+        if (e.rank == 0) ue_mma<0>(L, e.tmem, 1, GRAD); else ue_relay(L, 1, GRAD);
+    } else if (e.warp == 9) {
         ue_producer(L, blob, e.rank, 1, GRAD);
+    } else if (e.rank == 0) {
+        ue_mma<1>(L, e.tmem, 1, GRAD);
     }
     ue_teardown(e);
 }
@@ -1138,9 +1154,11 @@ k_hmc_step_u(ULayout L, const uint8_t* __restrict__ blob, fab_target_desc tgt, f
                 }
             }
         } else if (e.warp == 8) {
-            if (e.rank == 0) ue_mma(L, e.tmem, a.L, true); else ue_relay(L, a.L, true);
-        } else {
+            if (e.rank == 0) ue_mma<0>(L, e.tmem, a.L, true); else ue_relay(L, a.L, true);
+        } else if (e.warp == 9) {
             ue_producer(L, blob, e.rank, a.L, true);
+        } else if (e.rank == 0) {
+            ue_mma<1>(L, e.tmem, a.L, true);
         }
     }
     __syncthreads();

@@ -1,6 +1,8 @@
 """Device timings of the other BASELINE.json configs (parity-test cases, not bench.py lines):
 
   C1  GMM-40 d=2, RealNVP 4x80, 8 distributions, Metropolis x1, batch 512       (+ CPU port)
+  C3s Many-Well-32 as config 3 (batch 16384) on ONE GPU: the strong-scaling reference point for the
+      8-GPU line of bench.py (16384 = 8 x 2048) and the batch where every SM carries row tiles
   C4  Many-Well-128, RealNVP 10x1280, 32 distributions, HMC L=10, the 512-particle shard one of
       8 GPUs carries for batch 4096
   C5  ALDP surrogate d=60, RealNVP 10x300, 20 distributions, HMC L=4, batch 1024, feeding the
@@ -77,6 +79,21 @@ def c1():
     return out
 
 
+def c3_strong():
+    import bench
+    out = []
+    for B in (2048, 16384):
+        flow, target, op, ais = bench.build_gpu(dict(bench.CFG), dev, None)
+        ms = timed(lambda: ais.sample_and_log_weights(B), 3, 10)
+        k_ms = ais.time_transitions(B, repeats=2)
+        Ff = bench.flops_per_particle_flow_pass(32, 10, 320)
+        out.append(dict(config=f"C3s manywell32_realnvp10x320_M16_hmcL5 batch {B} on ONE GPU", ms_per_call=ms,
+                        particles_per_s=B / ms * 1e3, k_hmc_step_ms=k_ms,
+                        k_hmc_step_algorithmic_tflops=2 * Ff * 5 * B / k_ms / 1e9,
+                        engine="rowtile" if flow.use_rowtile(B) else "warp"))
+    return out
+
+
 def c4():
     torch.manual_seed(0)
     flow = fb.B200RealNVP(128, 10, 10); randomize(flow, 0.003); flow = flow.to(dev)
@@ -121,5 +138,7 @@ def c5():
 
 
 if __name__ == "__main__":
-    for fn in (c1, c4, c5):
-        print(json.dumps(fn()), flush=True)
+    for fn in (c1, c3_strong, c4, c5):
+        r = fn()
+        for item in (r if isinstance(r, list) else [r]):
+            print(json.dumps(item), flush=True)
