@@ -533,13 +533,16 @@ __device__ __forceinline__ void ue_row_sum2(const ULayout& L, UCw& c, float& a, 
     b = ((e2[c.r] + e2[UE_ROWS + c.r]) + e2[2 * UE_ROWS + c.r]) + e2[3 * UE_ROWS + c.r];
 }
 // Sum of squares of a hidden operand row, handed from the epilogue that wrote the operand to the
-// epilogue of the GEMM that consumes it (no barrier: the consumer runs after accumulators that
-// every writer's operand-ready arrival precedes; two alternating buffers keep a fast thread's next
-// hand-off away from a slow thread's read).
+// epilogue of the GEMM that consumes it.  The consumer runs after accumulators that every writer's
+// operand-ready arrival precedes, so the values are long in place; the CTA barrier in ue_ssq_get makes
+// that ordering explicit (all compute threads have just passed the same accumulator wait, it costs
+// ~0.5 % of a layer) and two alternating buffers keep a fast thread's next hand-off away from a slow
+// thread's read.
 __device__ __forceinline__ void ue_ssq_put(const ULayout& L, UCw& c, float v) {
     reinterpret_cast<float*>(ue_smem + L.s_ssq)[(c.nq & 1) * (4 * UE_ROWS) + c.q * UE_ROWS + c.r] = v;
 }
 __device__ __forceinline__ float ue_ssq_get(const ULayout& L, UCw& c) {
+    ue_bar_compute();
     const float* p = reinterpret_cast<const float*>(ue_smem + L.s_ssq) + (c.nq & 1) * (4 * UE_ROWS) + c.r;
     ++c.nq;
     return ((p[0] + p[UE_ROWS]) + p[2 * UE_ROWS]) + p[3 * UE_ROWS];

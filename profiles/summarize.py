@@ -82,7 +82,7 @@ def main():
     for k, (c, ns) in sorted(by.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"| `{k}` | {c} | {ns / 1e6:.3f} | {100 * ns / tot:.1f} % |")
     lines += ["", f"own kernels per chain: {sum(v[0] for v in by.values())}; total {tot / 1e6:.2f} ms under ncu", ""]
-    lines += ["## `k_hmc_step` full capture (`--set full --clock-control none`)", ""]
+    lines += ["## dominant kernel, full capture (`--set full --clock-control none`)", ""]
     dr, dw = float(g("dram__bytes_read.sum")), float(g("dram__bytes_write.sum"))
     scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Gbyte": 1e9}
     dr *= scale.get(units.get("dram__bytes_read.sum"), 1)
@@ -94,7 +94,7 @@ def main():
               f"* L2: tex read sectors {g('lts__t_sectors_srcunit_tex_op_read.sum')} (x32 B), hit rate {g('lts__t_sector_hit_rate.pct')} %",
               f"* FMA pipe active {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')} %, issue slots busy "
               f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} %, warps active {g('sm__warps_active.avg.pct_of_peak_sustained_active')} % of max",
-              f"* tensor pipe (warp-level HMMA.1688.F32.TF32, 3xTF32): active {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} % of cycles; "
+              f"* tensor pipe ({(bench or {}).get('roofline', {}).get('pipe', 'see bench line')}): active {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} % of the active SMs' cycles; "
               f"ALU pipe {g('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active')} %; SM clock during the capture "
               f"{g('sm__cycles_elapsed.avg.per_second')} {units.get('sm__cycles_elapsed.avg.per_second')}",
               f"* instructions {g('smsp__inst_executed.sum')}; mix: " + ", ".join(f"{k} {100 * v:.1f} %" for k, v in ops.items()),
@@ -104,7 +104,7 @@ def main():
         lines += ["## bench.py line of the same build", "",
                   f"* value {bench['value']:.0f} particles/s ({bench['ms_per_step']:.2f} ms/step), e2e {bench['e2e']['value']:.0f} particles/s",
                   f"* `k_hmc_step` {r['kernel_ms']:.3f} ms/launch (CUDA events) -> {r['achieved']:.2f} TFLOP/s algorithmic = "
-                  f"{100 * r['pipe_frac']:.1f} % of the 3xTF32 mma.sync ceiling ({r['pipe_peak']:.1f} TF = measured HMMA issue rate / 3), "
+                  f"{100 * r['pipe_frac']:.1f} % of the engine's own ceiling on the SMs this batch occupies ({r['pipe_peak']:.1f} TF, see `pipe` in the bench line), "
                   f"{100 * r['frac']:.2f} % of the measured bf16 cuBLAS peak",
                   f"* kernel share of the step: {100 * bench['config']['M'] * r['kernel_ms'] / bench['ms_per_step']:.1f} % (events) vs "
                   f"{100 * sum(v[1] for k, v in by.items() if k.startswith('k_hmc_step')) / tot if tot else 0:.1f} % (ncu launch list)",
