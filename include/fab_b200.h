@@ -326,16 +326,21 @@ int fab_flow_param_grad_f32(const fab_flow_desc* flow, const float* d_blob, cons
  * many-well target; everything else stays on the warp-level engine above.
  *
  * Weight images ("ublob", bytes): [scalar block | layer 0 | layer 1 | ...].  Scalar block (fp32):
- * loc[32], log_scale[32], then per layer 8 floats: for the seven operand types t = 0..6 the
- * un-scaling factor (1/s_t)(1 + 1.67e-8 KS_t) and sum(log_S).  A layer block holds, for each
- * operand type and each CTA rank of the pair, the f16 image the tensor core reads:
- *     image[k-chunk c][row][8 halves]       (one "core matrix" = 8 rows x 16 bytes, no swizzle)
- * k-chunk c = logical k 8c..8c+7 (k == K: the bias row; beyond: zero).  Rows of a rank:
- *   wide types  (0: z->[h1pre|v], 1: h1->h2pre, 3: gparam->gh2, 4: gh2->gh1): for column block
- *     g = 0,1: N/4 rows "hi" then N/4 rows "lo" of the output columns owned by thread group
- *     q = 2g + rank, i.e. columns [q N/4, (q+1) N/4)   (type 0: W/4 hidden columns, then 8 v columns);
- *   narrow types (2: h2->[shift|scale], 5: gh1->g, 6: gv->g): N/2 rows "hi" then N/2 rows "lo" of
- *     columns 8 rank + (0..7), then 16 + 8 rank + (0..7).
+ * loc[32], log_scale[32], then per layer 16 floats: [0..6] the un-scaling factor 1/s_t of the seven
+ * operand types, [7] sum(log_S), [8..11] max_n ||M[:,n]||_2 of the wide types 0 (hidden columns), 1,
+ * 3, 4 and [12..13] max_n |bias_n| of types 0, 1 (the a-priori row scales of the hidden operands:
+ * |h_n| <= ||h_in||_2 ||M[:,n]||_2 + |b_n|).  A layer block holds, for each operand type and each CTA
+ * rank of the pair, the f16 image the tensor core reads, column block by column block, inside a block
+ * one slab per k-step in the order the issuer consumes them:
+ *     slab[2 k-chunks][rows of the block][8 halves]   (one "core matrix" = 8 rows x 16 bytes, no swizzle)
+ * k-chunk c = logical k 8c..8c+7 (k == K: the bias row; beyond: zero).  Consumption order of the
+ * k-steps of a type whose A operand is a hidden activation (1, 2, 4, 5): first half of the real
+ * k-steps, the bias step (types 1, 2), second half; other types: natural order.  Rows of a block:
+ *   wide types  (0: z->[h1pre|v], 1: h1->h2pre, 3: gparam->gh2, 4: gh2->gh1), column block g = 0,1:
+ *     N/4 rows "hi" then N/4 rows "lo" of the output columns [q N/4, (q+1) N/4), q = 2g + rank
+ *     (type 0: W/4 hidden columns, then the 8 v columns 8q..8q+7);
+ *   narrow types (2: h2->[shift|scale], 5: gh1->g, 6: gv->g), one block: N/2 rows "hi" then N/2 rows
+ *     "lo" of columns 8 rank + (0..7), then 16 + 8 rank + (0..7).
  * value = hi + lo = M[k][n] * s_t, s_t = the power of two that puts max|M| in [2^13, 2^14).
  * The images are produced on the device by fab_umma_pack_f32 from a plain fp32 buffer:
  * [loc | log_scale | per layer: M_0 [K_0][N_0], bias_0 [N_0], M_1, bias_1, M_2, bias_2, M_3 .. M_6,

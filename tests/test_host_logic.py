@@ -117,3 +117,14 @@ def test_point_mask_semantics():
     pt[m] = other[m]
     assert torch.equal(pt.log_q, torch.tensor([-1., 1., -1.]))
     assert torch.equal(pt.grad_log_p[1], torch.ones(2)) and torch.equal(pt.grad_log_p[0], -torch.ones(2))
+
+
+def test_state_dict_keys_follow_normflows_fixture():
+    """checkpoints written by FABModel.save (core.py:222-260) must keep the key names
+    normflows gives the reference's flow; the fixture lists them explicitly so that a rename fails here."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "normflows_state_dict_keys.json")))
+    import fab_torch_b200 as fb
+    flow = fb.B200RealNVP(4, fx["n_flow_layers"], 3)
+    assert sorted(flow.state_dict().keys()) == fx["keys"]
