@@ -432,7 +432,10 @@ def run_gpu_arm(args):
                     config=config_block(cfg, world),
                     engine=dict(hmc_step="row-tile tcgen05 (f16 hi/lo operands, fp32 accumulate)" if rowtile
                                 else "warp-level mma.sync 3xTF32 (weights rounded to 22 bits)",
-                                cuda_graph=bool(ais.use_cuda_graph)),
+                                cuda_graph=bool(ais.use_cuda_graph),
+                                tuner_exchange=("none (one rank)" if world == 1 else
+                                                "NVLink peer memory (fab_hmc_finish_peer_f32)" if getattr(op, "_peer", None) is not None
+                                                else "NCCL all-reduce")),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d * world,
                              d2h_bytes_per_step=d2h * world, ms_per_step=total_e2e_ms / args.steps),
                     gpu_launches=launches_per_step * args.steps, clocks=clock_rec, roofline=roof,

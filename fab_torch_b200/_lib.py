@@ -103,6 +103,8 @@ SIGNATURES = {
     "fab_buffer_topk_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "fab_buffer_adjust_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
     # row-tile engine (tcgen05 / TMEM / TMA)
+    "fab_hmc_peer_buffer_bytes": (C.c_int64, [C.c_int32]),
+    "fab_hmc_finish_peer_f32": (C.c_int, [HmcState, HmcArgs, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "fab_flow_param_grad_layout": (C.c_int, [C.POINTER(FlowDesc), C.c_int64, C.POINTER(C.c_int64)]),
     "fab_flow_logprob_tape_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, _P, _P, _P, C.c_int64, _P]),
     "fab_flow_param_grad_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, _P, C.c_int64, _P, _P, _P]),

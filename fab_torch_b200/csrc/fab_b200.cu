@@ -388,6 +388,21 @@ int fab_hmc_finish_f32(fab_hmc_state st, fab_hmc_args a, const float* d_stats, v
     return FAB_OK;
 }
 
+int64_t fab_hmc_peer_buffer_bytes(int32_t world) {
+    if (world < 1 || world > 32) return fail(FAB_E_INVALID, "fab_hmc_peer_buffer_bytes: world must be 1..32");
+    return (int64_t)FAB_PEER_RING * world * 8 * (int64_t)sizeof(float);
+}
+
+int fab_hmc_finish_peer_f32(fab_hmc_state st, fab_hmc_args a, const float* d_stats, float* const* d_peer_bufs,
+                            int32_t world, int32_t rank, uint32_t* d_seq, void* stream) {
+    if (!st.d_epsilons || !st.d_common_epsilon || !st.d_log || !d_stats || !d_peer_bufs || !d_seq || world < 1 ||
+        world > 32 || rank < 0 || rank >= world)
+        return fail(FAB_E_INVALID, "fab_hmc_finish_peer_f32: bad arguments (world <= 32)");
+    k_hmc_finish_peer<<<1, 32, 0, (cudaStream_t)stream>>>(st, a, d_stats, d_peer_bufs, world, rank, d_seq);
+    CK_LAUNCH("k_hmc_finish_peer");
+    return FAB_OK;
+}
+
 int64_t fab_metropolis_workspace_bytes(const fab_flow_desc* flow, int64_t n, int32_t n_updates) {
     (void)flow; (void)n_updates;
     if (n < 0) return FAB_E_INVALID;

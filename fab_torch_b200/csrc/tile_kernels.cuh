@@ -178,6 +178,54 @@ k_ais_init(TileLayout L, fab_flow_desc f, const float* __restrict__ blob, fab_ta
     }
 }
 
+// Tuner statistics exchanged over NVLink peer memory instead of an NCCL all-reduce (the
+// (sum of clamped acceptance, count, distance) triple of hmc.py:122-123,162-170 summed over the ranks,
+// then the identical update on every rank).  Every rank owns a symmetric buffer
+//     slot[FAB_PEER_RING][world][8 floats]    (3 statistics, pad, sequence flag, pad)
+// mapped into all peers.  Exchange number s (a device-resident counter, so the launch can sit in a
+// captured CUDA graph): lane r stores this rank's triple into slot[s % RING][my rank] of peer r,
+// fences, stores the flag s + 1; then lane r spins on slot[s % RING][r] of the LOCAL buffer until
+// rank r's flag arrives and reads its triple.  The triples are added in rank order, so every rank gets
+// the same bits (and the same as the all-reduce of the single-process sum order is NOT required: the
+// tuner only compares log(mean) with a threshold).  A rank is at most one exchange ahead of any
+// peer (it cannot finish exchange s + 1 without that peer's s + 1 flag), so RING >= 2 keeps a fast
+// rank's next store away from a slow rank's read.  A flag that does not arrive within ~4 s traps
+// instead of hanging the GPU.
+#define FAB_PEER_RING 4
+__global__ void k_hmc_finish_peer(fab_hmc_state st, fab_hmc_args a, const float* __restrict__ stats,
+                                  float* const* __restrict__ peer_bufs, int world, int rank,
+                                  unsigned int* __restrict__ seq_counter) {
+    __shared__ float s_sum[3][32];
+    const int r = threadIdx.x;
+    const unsigned int seq = *seq_counter;
+    const size_t slot = (size_t)(seq % FAB_PEER_RING) * world;
+    if (r < world) {
+        float* dst = peer_bufs[r] + (slot + rank) * 8;
+        dst[0] = stats[0]; dst[1] = stats[1]; dst[2] = stats[2];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(dst + 4) = seq + 1u;
+        const float* src = peer_bufs[rank] + (slot + r) * 8;
+        const volatile unsigned int* flag = reinterpret_cast<const volatile unsigned int*>(src + 4);
+        const long long t0 = clock64();
+        while (*flag != seq + 1u) {
+            if (clock64() - t0 > 8000000000ll) {
+                printf("k_hmc_finish_peer: rank %d waited 4 s for rank %d (exchange %u)\n", rank, r, seq);
+                __trap();
+            }
+        }
+        __threadfence_system();
+        const volatile float* vs = src;
+        s_sum[0][r] = vs[0]; s_sum[1][r] = vs[1]; s_sum[2][r] = vs[2];
+    }
+    __syncthreads();
+    if (r == 0) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int q = 0; q < world; ++q) { s0 += s_sum[0][q]; s1 += s_sum[1][q]; s2 += s_sum[2][q]; }
+        hmc_finish(st, a, s0, s1, s2);
+        *seq_counter = seq + 1u;
+    }
+}
+
 __global__ void k_hmc_finish(fab_hmc_state st, fab_hmc_args a, const float* __restrict__ stats) {
     if (threadIdx.x == 0 && blockIdx.x == 0) hmc_finish(st, a, stats[0], stats[1], stats[2]);
 }

@@ -66,3 +66,48 @@ def merge_ess_partials(parts: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor,
     S2 = (s2 * scale * scale).sum()
     N = cnt.sum()
     return S1 * S1 / (S2 * N), M + torch.log(S1), N
+
+
+class PeerExchange:
+    """Symmetric exchange buffers for the tuner statistics (`fab_hmc_finish_peer_f32`): every rank's
+    buffer is mapped into all peers (torch symmetric memory over NVLink), the kernel stores its triple
+    into the peers and sums theirs -- no NCCL launch between two transitions.  `create` returns None
+    when the group is not an NCCL group of CUDA devices on one node, when symmetric memory is not
+    available, or with FAB_PEER_EXCHANGE=0; the decision is all-reduced so that every rank takes the
+    same path."""
+
+    def __init__(self, buf, handle, ptrs, seq, world_size, rank):
+        self.buf, self.handle, self.ptrs, self.seq = buf, handle, ptrs, seq
+        self.world, self.rank = world_size, rank
+
+    @staticmethod
+    def create(group, device) -> Optional["PeerExchange"]:
+        import os
+        import torch.distributed as dist
+        w, r = world(group)
+        if w == 1 or device.type != "cuda" or dist.get_backend(group) != "nccl":
+            return None
+        ok, made = 1, None
+        if os.environ.get("FAB_PEER_EXCHANGE", "1") == "0" or w > 32:
+            ok = 0
+        else:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                from fab_torch_b200 import _lib
+                nbytes = int(_lib.lib().fab_hmc_peer_buffer_bytes(w))
+                _lib.check(nbytes, "fab_hmc_peer_buffer_bytes")
+                buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+                buf.zero_()
+                handle = symm_mem.rendezvous(buf, group.group_name)
+                ptrs = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=device)
+                seq = torch.zeros(1, dtype=torch.int32, device=device)
+                made = PeerExchange(buf, handle, ptrs, seq, w, r)
+            except Exception as e:           # noqa: BLE001 -- any failure means "use the all-reduce"
+                ok = 0
+                if r == 0:
+                    print(f"[fab_torch_b200] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)             # every buffer is zeroed before anybody stores into it
+        return made if int(flag.item()) == 1 else None

@@ -160,6 +160,15 @@ class TransitionOperator(nn.Module):
     def _world(self) -> int:
         return fdist.world(self.process_group)[0]
 
+    def _peer_exchange(self, dev):
+        """NVLink peer-memory exchange of the tuner statistics (dist.PeerExchange), or None -> NCCL.
+        Created on the first multi-rank transition (collective: every rank gets here together)."""
+        key = (id(self.process_group), str(dev))
+        if getattr(self, "_peer_key", None) != key:
+            self._peer = fdist.PeerExchange.create(self.process_group, dev)
+            self._peer_key = key
+        return self._peer
+
     @staticmethod
     def _check_point(point: Point, need_grad: bool):
         for name in ("x", "log_q", "log_p") + (("grad_log_q", "grad_log_p") if need_grad else ()):
@@ -346,9 +355,15 @@ class HamiltonianMonteCarlo(TransitionOperator):
                 e1.record()
                 timings.append((e0, e1))
             if world > 1:
-                fdist.reduce_stats(self._stats[:4], self.process_group)
-                _lib.check(L.fab_hmc_finish_f32(st, args, _lib.ptr(self._stats), stream),
-                           "fab_hmc_finish_f32")
+                px = self._peer_exchange(dev)
+                if px is not None:      # statistics summed over NVLink peer memory inside one small launch
+                    _lib.check(L.fab_hmc_finish_peer_f32(st, args, _lib.ptr(self._stats), _lib.ptr(px.ptrs),
+                                                         px.world, px.rank, _lib.ptr(px.seq), stream),
+                               "fab_hmc_finish_peer_f32")
+                else:
+                    fdist.reduce_stats(self._stats[:4], self.process_group)
+                    _lib.check(L.fab_hmc_finish_f32(st, args, _lib.ptr(self._stats), stream),
+                               "fab_hmc_finish_f32")
             prop_in = prop_out
         if i == 1:
             self._seen_first = True

@@ -215,6 +215,16 @@ int fab_hmc_step_f32(const fab_flow_desc* flow, const float* d_blob, const fab_t
 
 /* Multi-GPU tail of an outer step: d_stats holds the all-reduced (sum_exp, count, dist_sum). */
 int fab_hmc_finish_f32(fab_hmc_state st, fab_hmc_args args, const float* d_stats, void* stream);
+/* The same update with the statistics summed over the ranks INSIDE the launch, over peer-mapped
+ * memory (NVLink) instead of an NCCL all-reduce between two launches: d_peer_bufs[r] = rank r's
+ * symmetric exchange buffer (fab_hmc_peer_buffer_bytes(world) bytes, zero on first use) as mapped in
+ * this process, d_seq = a device-resident exchange counter (zero on first use; every rank must issue
+ * the same sequence of calls).  Capturable in a CUDA graph.  Replaces hmc.py:122-123,162-170 for a
+ * rank-sharded batch. */
+int64_t fab_hmc_peer_buffer_bytes(int32_t world);
+int fab_hmc_finish_peer_f32(fab_hmc_state st, fab_hmc_args args, const float* d_stats,
+                            float* const* d_peer_bufs, int32_t world, int32_t rank, uint32_t* d_seq,
+                            void* stream);
 
 /* Metropolis (metropolis.py:51-74): all n_updates of one transition in one launch. */
 typedef struct fab_metropolis_args {
