@@ -39,12 +39,13 @@
 //     owned scratch buffer (L2 resident).
 //
 // Warp roles (352 threads): warps 0-7 compute (epilogues, coupling, leapfrog, accept); warps 8 and
-// 10 of the leader CTA issue the MMAs -- TWO issuers, because one thread issues at most one
-// tcgen05.mma per ~45 cycles plus its address arithmetic (~73 cycles per MMA measured) while these
-// small MMAs (M 128 x N 160 x K 16 per pair) execute in ~45: warp 8 issues the hi*hi product of the
-// wide GEMMs and the narrow GEMMs, warp 10 the two cross products (their own accumulator, so the two
-// instruction streams never order against each other); both run the same issue program and commit
-// every barrier.  Warp 8 of the peer CTA relays "my half of the weights has landed" to the leader;
+// 10 of the leader CTA issue the MMAs -- TWO issuers, because walking the issue program costs one
+// thread ~350 cycles per weight stage on top of the MMAs (~73 cycles per MMA measured) while these
+// small MMAs (M 128 x N 160 x K 16 per pair) execute in 40: warp 8 owns column block 0 of the wide
+// GEMMs and the narrow GEMMs, warp 10 column block 1 (separate accumulators, so the two instruction
+// streams never order against each other); the weight stages of the two blocks alternate in the
+// ring, each issuer walks its own program and frees its own stages, both commit the accumulator
+// barriers.  Warp 8 of the peer CTA relays "my half of the weights has landed" to the leader;
 // warp 9 lane 0 streams weight stages global -> shared with cp.async.bulk.
 #pragma once
 #include <cuda_fp16.h>
@@ -103,8 +104,9 @@ struct UOp {
     uint32_t nbh;      // wide: distance from the hi to the lo rows of the B block >> 4 (rows x 16 B)
     uint32_t idesc0, idesc1;
     uint32_t count, flags;
+    uint32_t it_rel;   // weight stage of this entry, counted from the first stage of the layer's (forward / gradient) program
 };
-#define UE_MAX_OPS 48
+#define UE_MAX_OPS 40
 
 struct ULayout {
     int d, W, K, WQ;
@@ -116,8 +118,11 @@ struct ULayout {
     int s_h, s_z, s_par, s_gv, s_ring, s_ex, s_ssq, s_bar, smem_bytes;
     int hplane, zplane, pplane;
     float dl[8];     // truncation compensation: [0] v columns of type 0, [1] h1pre of type 0, [2..7] types 1..6
-    int n_ops_fwd, n_ops;      // issue program: ops[0, n_ops_fwd) forward groups of a layer, [n_ops_fwd, n_ops) gradient groups
-    UOp ops[UE_MAX_OPS];
+    // issue programs of the two issuer warps (issuer g owns column block g of the wide GEMMs, issuer 0 the
+    // narrow ones): ops[r][0, n_ops_fwd[r]) forward groups of a layer, [n_ops_fwd[r], n_ops[r]) gradient groups
+    int n_ops_fwd[2], n_ops[2];
+    int n_stages_fwd, n_stages_bwd;      // weight stages per layer in the forward / gradient program
+    UOp ops[2][UE_MAX_OPS];
 };
 
 __host__ inline bool umma_supported(int d, int W, int K) { return d == 32 && W % 64 == 0 && W >= 64 && W <= 320 && K >= 1 && K <= 10; }
@@ -190,17 +195,19 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
     L.dl[0] = 4.5e-8f;     // calibrated on log q of a 10-layer flow (one FMA rounds up for ~60 % of the mantissas)
     L.dl[1] = UE_TRUNC_PER_ACC * (float)L.t[0].KS;
     for (int i = 1; i < 7; ++i) L.dl[1 + i] = UE_TRUNC_PER_ACC * (float)L.t[i].KS;
-    // ---- MMA issue program (order: header comment "MMA / epilogue overlap"; the weight stages are
-    // consumed in exactly the order ue_for_each_stage produces them) ----
-    int no = 0;
+    // ---- MMA issue programs.  Stream order of the weight stages (ue_for_each_stage): per operand type
+    // stage by stage, for a wide type block 0's stage then block 1's; issuer g consumes block g's. ----
+    int no[2] = {0, 0}, stage = 0;
     auto group = [&](int t0, int t1) {
-        bool first = true, a1 = false;
+        bool first[2] = {true, true}, a1[2] = {false, false};
+        const bool wide_group = L.t[t0].wide != 0;
         for (int ti = t0; ti <= t1; ++ti) {
             const UType& t = L.t[ti];
             // boundaries inside the consumption order where a run must end
             const int kb0 = t.hin && t.bias ? t.KSr / 2 : t.KS, kb1 = t.hin && t.bias ? kb0 + 1 : t.KS;
-            for (int g = 0; g < t.nblk; ++g)
-                for (int j0 = 0; j0 < t.KS; j0 += t.ksps) {
+            for (int j0 = 0; j0 < t.KS; j0 += t.ksps)
+                for (int g = 0; g < t.nblk; ++g) {
+                    const int r = g;                           // the issuer of this block
                     const int j1 = j0 + t.ksps < t.KS ? j0 + t.ksps : t.KS;
                     int ja = j0;
                     while (ja < j1) {
@@ -208,7 +215,7 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
                         if (ja < kb0 && kb0 < jb) jb = kb0;
                         if (ja < kb1 && kb1 < jb) jb = kb1;
                         if (ja < t.kfirst && t.kfirst < jb) jb = t.kfirst;
-                        UOp& o = L.ops[no++];
+                        UOp& o = L.ops[r][no[r]++];
                         o = UOp{};
                         o.a = (uint32_t)(t.a_off >> 4) + (uint32_t)ue_kstep(t, ja) * 128u + ((1024u >> 4) << 16);
                         o.b = (uint32_t)(ja - j0) * (uint32_t)t.Rb * 2u + (((uint32_t)t.Rb * 16u >> 4) << 16);
@@ -219,25 +226,46 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
                         o.d1 = o.d0 + (uint32_t)t.nbh;
                         o.idesc0 = t.idesc_a; o.idesc1 = t.wide ? t.idesc_a : t.idesc_b;
                         o.count = (uint32_t)(jb - ja);
+                        o.it_rel = (uint32_t)stage;
                         uint32_t f = (t.wide ? UOP_WIDE : 0u) | (ja > 0 ? UOP_ACC : 0u);
-                        if (first) { f |= UOP_WAIT_A0; if (!t.hin) { f |= UOP_WAIT_A1; a1 = true; } first = false; }
-                        if (!a1 && ja >= t.kfirst) { f |= UOP_WAIT_A1; a1 = true; }
+                        // block 1 overwrites accumulators that the previous group's second epilogue reads: it waits
+                        // for both operand halves before its first MMA; block 0 / narrow types wait for the second
+                        // half only where they reach it
+                        if (first[r]) {
+                            f |= UOP_WAIT_A0;
+                            if (!t.hin || g == 1) { f |= UOP_WAIT_A1; a1[r] = true; }
+                            first[r] = false;
+                        }
+                        if (!a1[r] && ja >= t.kfirst) { f |= UOP_WAIT_A1; a1[r] = true; }
                         if (ja == j0) f |= UOP_NEWSTAGE;
                         if (jb == j1) f |= UOP_FREE;
-                        // block 0's epilogue may start: hidden input -> after (blk1, k-half 0 + bias), d-wide input -> after blk0
-                        if (t.wide && t.hin && g == 1 && jb == t.kfirst) f |= UOP_D0;
-                        if (t.wide && !t.hin && g == 0 && jb == t.KS) f |= UOP_D0;
-                        if (ti == t1 && g == t.nblk - 1 && jb == t.KS) f |= UOP_D1;
+                        // D0 (block 0 complete and the first operand half no longer read; both issuers commit it):
+                        // issuer 0 after its last k-step, issuer 1 after (blk1, k-half 0 + bias) -- for a d-wide input
+                        // after its only stage
+                        if (t.wide && g == 0 && jb == t.KS) f |= UOP_D0;
+                        if (t.wide && g == 1 && jb == (t.hin ? t.kfirst : t.KS)) f |= UOP_D0;
+                        // D1 (group complete; both issuers commit it)
+                        if (ti == t1 && jb == t.KS) f |= UOP_D1;
                         o.flags = f;
                         ja = jb;
                     }
+                    ++stage;
                 }
+        }
+        if (!wide_group) {
+            // issuer 1 has no MMAs in a narrow group: an empty entry commits D1 for it -- AFTER the group's
+            // operand barriers (they complete after the previous group's D1, so the two arrivals of one
+            // D1 phase always come from the two issuers)
+            UOp& o = L.ops[1][no[1]++];
+            o = UOp{};
+            o.flags = UOP_WAIT_A0 | UOP_WAIT_A1 | UOP_D1;
         }
     };
     group(0, 0); group(1, 1); group(2, 2);
-    L.n_ops_fwd = no;
+    L.n_ops_fwd[0] = no[0]; L.n_ops_fwd[1] = no[1]; L.n_stages_fwd = stage;
+    stage = 0;
     group(3, 3); group(4, 4); group(5, 6);
-    L.n_ops = no;
+    L.n_ops[0] = no[0]; L.n_ops[1] = no[1]; L.n_stages_bwd = stage;
     return L;
 }
 
@@ -373,7 +401,8 @@ __device__ __forceinline__ void ue_for_each_group(const ULayout& L, bool grad, F
     for (int k = L.K - 1; k >= 0; --k) { f(k, 0, 0); f(k, 1, 1); f(k, 2, 2); }
     if (grad) for (int k = 0; k < L.K; ++k) { f(k, 3, 3); f(k, 4, 4); f(k, 5, 6); }
 }
-// The weight stages of `n_evals` evaluations in consumption order: f(type, layer, block, first k-step
+// The weight stages of `n_evals` evaluations in stream order (per type stage by stage, block 0's stage then
+// block 1's): f(type, layer, block, first k-step
 // (consumption index), k-steps in the stage, running stage index)
 template <class F>
 __device__ __forceinline__ void ue_for_each_stage(const ULayout& L, int n_evals, bool grad, F f) {
@@ -382,8 +411,8 @@ __device__ __forceinline__ void ue_for_each_stage(const ULayout& L, int n_evals,
         ue_for_each_group(L, grad, [&](int k, int t0, int t1) {
             for (int ti = t0; ti <= t1; ++ti) {
                 const UType& t = L.t[ti];
-                for (int g = 0; g < t.nblk; ++g)
-                    for (int j0 = 0; j0 < t.KS; j0 += t.ksps) { f(t, k, g, j0, min(t.ksps, t.KS - j0), it); ++it; }
+                for (int j0 = 0; j0 < t.KS; j0 += t.ksps)
+                    for (int g = 0; g < t.nblk; ++g) { f(t, k, g, j0, min(t.ksps, t.KS - j0), it); ++it; }
             }
         });
 }
@@ -429,10 +458,10 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
     const uint32_t dhi = (128u >> 4) | (1u << 14);        // descriptor high word: SBO = 128 B, version 1
     auto desc = [&](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
     const uint32_t lead = umma::elect_one() ? 1u : 0u;      // the lane whose MMAs and commits are issued
-    uint32_t it = 0, gi = 0, sb4 = 0;
+    uint32_t it_base = 0, gi = 0, sb4 = 0, slot = 0;
     auto run = [&](int e0, int e1) {
         for (int e = e0; e < e1; ++e) {
-            const UOp& o = L.ops[e];
+            const UOp& o = L.ops[ROLE][e];
             const uint32_t f = o.flags;
             if (f & UOP_WAIT_A0) {
                 UE_T0(); umma::mbar_wait_cluster(B.aready, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
@@ -441,10 +470,9 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
                 UE_T0(); umma::mbar_wait_cluster(B.aready + 1, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
             }
             if (f & UOP_NEWSTAGE) {
-                // (a helper warp that watches the stage barriers and publishes a counter for the issuers was
-                // measured: no gain once there are two issuers, 0.7811 vs 0.7813 ms per launch)
-                const uint32_t slot = it % UE_NSTAGE, par = (it / UE_NSTAGE) & 1;
-                UE_T0(); umma::mbar_wait_cluster(B.full + slot, par); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
+                const uint32_t it = it_base + o.it_rel;
+                slot = it % UE_NSTAGE;
+                UE_T0(); umma::mbar_wait_cluster(B.full + slot, (it / UE_NSTAGE) & 1); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
                 sb4 = ring4 + slot * (UE_STAGE_BYTES >> 4);
             }
             if (f & (UOP_WAIT_A0 | UOP_WAIT_A1 | UOP_NEWSTAGE)) umma::tc_fence_after();
@@ -452,20 +480,22 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
                 UE_T0();
                 uint32_t ah = sbase4 + o.a, bk = sb4 + o.b, acc = (f & UOP_ACC) ? 1u : 0u;
                 const uint32_t al = o.a_lo, kstr = o.kstr, d0 = tmem + o.d0, d1 = tmem + o.d1, id0 = o.idesc0, id1 = o.idesc1, nbh = o.nbh;
+#ifdef UE_X_NOMMA
+                if (false) {
+#else
                 if (f & UOP_WIDE) {
-                    if (ROLE == 0) {
-                        for (uint32_t n = o.count; n > 0; --n) {
-                            umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // main   = hi * hi
-                            ah += 128; bk += kstr; acc = 1u;
-                        }
-                    } else {
-                        for (uint32_t n = o.count; n > 0; --n) {
-                            umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id0, acc, lead);           // cross  = lo * hi
-                            umma::mma_ss2_pred(d1, desc(ah), desc(bk + nbh), id0, 1u, lead);           // cross += hi * lo
-                            ah += 128; bk += kstr; acc = 1u;
-                        }
+#endif
+                    for (uint32_t n = o.count; n > 0; --n) {
+                        umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id0, acc, lead);           // cross  = lo * hi
+                        umma::mma_ss2_pred(d1, desc(ah), desc(bk + nbh), id0, 1u, lead);           // cross += hi * lo
+                        umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // main   = hi * hi
+                        ah += 128; bk += kstr; acc = 1u;
                     }
-                } else if (ROLE == 0) {
+#ifdef UE_X_NOMMA
+                } else if (false) {
+#else
+                } else {
+#endif
                     for (uint32_t n = o.count; n > 0; --n) {
                         umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // [hi*hi | hi*lo]
                         umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id1, 1u, lead);            // += lo*hi
@@ -474,18 +504,15 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
                 }
                 UE_ACC(4, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
             }
-            if (f & UOP_FREE) {
-                if (lead) umma::mma_commit<2>(B.empty + (it % UE_NSTAGE), 3);
-                ++it;
-            }
+            if (f & UOP_FREE) { if (lead) umma::mma_commit<2>(B.empty + slot, 3); }
             if (f & UOP_D0) { if (lead) umma::mma_commit<2>(B.dfull, 3); }
             if (f & UOP_D1) { if (lead) umma::mma_commit<2>(B.dfull + 1, 3); ++gi; }
             __syncwarp();
         }
     };
     for (int ev = 0; ev < n_evals; ++ev) {
-        for (int k = 0; k < L.K; ++k) run(0, L.n_ops_fwd);
-        if (grad) for (int k = 0; k < L.K; ++k) run(L.n_ops_fwd, L.n_ops);
+        for (int k = 0; k < L.K; ++k) { run(0, L.n_ops_fwd[ROLE]); it_base += L.n_stages_fwd; }
+        if (grad) for (int k = 0; k < L.K; ++k) { run(L.n_ops_fwd[ROLE], L.n_ops[ROLE]); it_base += L.n_stages_bwd; }
     }
 }
 
@@ -643,6 +670,9 @@ __device__ __forceinline__ void ue_acc8(uint32_t ta_main, uint32_t ta_cross, flo
 template <bool FWD, int NC8, int G>
 __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uint32_t ta_main, uint32_t ta_cross, float sc,
                                              uint32_t (&mask)[3], float& ssq) {
+#ifdef UE_X_NOEPI
+    return;
+#endif
     uint8_t* hp = ue_smem + L.s_h;
     const int chunk0 = ((2 * G + c.h) * L.WQ) / 8 + c.g * NC8;
     // software-pipelined over the chunks: the loads of chunk j+1 are in flight while chunk j is scaled /
@@ -947,7 +977,7 @@ __device__ __forceinline__ UEnv ue_setup(const ULayout& L) {
     for (int i = threadIdx.x; i < L.s_ring / 16; i += UE_THREADS) reinterpret_cast<uint4*>(ue_smem)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         const UBars B = ue_bars(L);
-        for (int s = 0; s < UE_NSTAGE; ++s) { umma::mbar_init(B.full + s, e.rank == 0 ? 2 : 1); umma::mbar_init(B.empty + s, 2); }
+        for (int s = 0; s < UE_NSTAGE; ++s) { umma::mbar_init(B.full + s, e.rank == 0 ? 2 : 1); umma::mbar_init(B.empty + s, 1); }
         umma::mbar_init(B.dfull, 2); umma::mbar_init(B.dfull + 1, 2);      // one commit per issuer
         umma::mbar_init(B.aready, 16); umma::mbar_init(B.aready + 1, 16);
         umma::mbar_fence_init();
