@@ -61,6 +61,15 @@ class HmcArgs(C.Structure):
                 ("defer_stats", C.c_int32)]
 
 
+class ChainHmcArgs(C.Structure):
+    _fields_ = [("n_dist", C.c_int32), ("n_outer", C.c_int32), ("L", C.c_int32), ("tune", C.c_int32),
+                ("with_logging", C.c_int32), ("use_rowtile", C.c_int32),
+                ("target_p_accept", C.c_float), ("max_grad", C.c_float),
+                ("op_gammas", C.POINTER(Gamma)), ("w_gammas", C.POINTER(Gamma)),
+                ("w_update", C.POINTER(C.c_uint8)),
+                ("d_mom", C.POINTER(C.c_void_p)), ("d_exp", C.POINTER(C.c_void_p))]
+
+
 class MetropolisArgs(C.Structure):
     _fields_ = [("i", C.c_int32), ("n_updates", C.c_int32), ("tune", C.c_int32),
                 ("target_p_accept", C.c_float), ("g", Gamma), ("update_log_w", C.c_int32),
@@ -103,6 +112,10 @@ SIGNATURES = {
     "fab_buffer_topk_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "fab_buffer_adjust_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
     # row-tile engine (tcgen05 / TMEM / TMA)
+    "fab_ais_chain_workspace_bytes": (C.c_int64, [C.POINTER(FlowDesc), C.c_int64, C.c_int32, C.c_int32]),
+    "fab_ais_chain_hmc_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, C.POINTER(TargetDesc), HmcState,
+                                        C.POINTER(ChainHmcArgs), _P, PointPtrs, _P, _P, _P, _P, _P, _P, _P,
+                                        C.c_int64, _P]),
     "fab_hmc_peer_buffer_bytes": (C.c_int64, [C.c_int32]),
     "fab_hmc_finish_peer_f32": (C.c_int, [HmcState, HmcArgs, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "fab_flow_param_grad_layout": (C.c_int, [C.POINTER(FlowDesc), C.c_int64, C.POINTER(C.c_int64)]),

@@ -151,6 +151,12 @@ class AnnealedImportanceSampler:
         valid = torch.empty(n, dtype=torch.uint8, device=dev)
         counts = torch.zeros(2, dtype=torch.int32, device=dev)
         rec = torch.zeros(8, dtype=torch.float32, device=dev)
+        M = self.n_intermediate_distributions
+        if self._c_chain_ok(op, timings):
+            # single rank + HMC: the whole chain through ONE C-ABI call (fab_ais_chain_hmc_f32)
+            chain_noise = noise[1] if noise is not None else op.chain_noise(M, n, d, dev)
+            self._run_chain_c(pt, log_w, log_q0, valid, counts, rec, eps, chain_noise, logging)
+            return pt, log_w, counts, rec
         g1 = make_gamma(self.B_space[1], self.alpha, self.p_target)
         rc = L.fab_ais_init_f32(flow.desc(), _lib.ptr(flow.blob()), target.target_desc(dev),
                                 _lib.ptr(eps.contiguous()), g1, 1 if with_grad else 0,
@@ -160,7 +166,6 @@ class AnnealedImportanceSampler:
         self._filter(pt, log_w, None, counts[0:1])                 # "chain init"
         if logging:
             self._ess(pt.log_p, pt.log_q, counts[0:1], rec[0:3])   # ESS over base weights
-        M = self.n_intermediate_distributions
         chain_noise = noise[1] if noise is not None else op.chain_noise(M, n, d, dev)
         kernel_timing = timings is not None and "timings" in op.run.__code__.co_varnames
         for j in range(1, M + 1):
@@ -187,6 +192,45 @@ class AnnealedImportanceSampler:
             dist.all_reduce(gcounts, group=self.process_group)
             rec[6:8] = gcounts
         return pt, log_w, counts, rec
+
+    def _c_chain_ok(self, op, timings) -> bool:
+        import os
+        from fab_torch_b200.transition_operators import HamiltonianMonteCarlo
+        return (timings is None and self._world()[0] == 1 and type(op) is HamiltonianMonteCarlo
+                and self._target is op._target and op._flow is self.base_distribution
+                and os.environ.get("FAB_C_CHAIN", "1") != "0")
+
+    def _run_chain_c(self, pt, log_w, log_q0, valid, counts, rec, eps, chain_noise, logging):
+        """ais.py:53-87 as one call into the library (same launches, in the same order, as the loop in
+        `_run_chain`; bit-identical results -- tests/test_gpu_ais.py::test_c_chain_equals_python_loop)."""
+        import ctypes as C
+        flow, op, target = self.base_distribution, self.transition_operator, self._target
+        dev = pt.x.device
+        n, d = pt.x.shape
+        L = _lib.lib()
+        M = self.n_intermediate_distributions
+        tdesc = target.target_desc(dev)
+        rowtile = tdesc.kind == _lib.FAB_TARGET_MANYWELL and flow.use_rowtile(n)
+        og = (_lib.Gamma * (M + 2))(*[make_gamma(self.B_space[j], op.alpha, op.p_target) for j in range(M + 2)])
+        wg = (_lib.Gamma * (M + 2))(*[make_gamma(self.B_space[j], self.alpha, self.p_target) for j in range(M + 2)])
+        wu = (C.c_uint8 * (M + 1))(*[0 if bool(self.B_space[j + 1] == self.B_space[j]) else 1 for j in range(M + 1)])
+        moms = [a.contiguous() for a, _ in chain_noise]
+        exps = [b.contiguous() for _, b in chain_noise]
+        pm = (C.c_void_p * M)(*[_lib.ptr(a) for a in moms])
+        pe = (C.c_void_p * M)(*[_lib.ptr(b) for b in exps])
+        args = _lib.ChainHmcArgs(M, op.n_outer, op.L, 0 if op.eval_mode else 1, 1 if logging else 0,
+                                 1 if rowtile else 0, op.target_p_accept, op.max_grad, og, wg, wu, pm, pe)
+        nbytes = int(L.fab_ais_chain_workspace_bytes(flow.desc(), n, op.n_outer, 1 if rowtile else 0))
+        _lib.check(nbytes, "fab_ais_chain_workspace_bytes")
+        ws = op._workspace(nbytes, dev)
+        rc = L.fab_ais_chain_hmc_f32(flow.desc(), _lib.ptr(flow.blob()),
+                                     _lib.ptr(flow.umma_blob()) if rowtile else None, tdesc, op._state(),
+                                     C.byref(args), _lib.ptr(eps.contiguous()), _lib.point_ptrs(pt), _lib.ptr(log_w),
+                                     _lib.ptr(log_q0), _lib.ptr(valid), _lib.ptr(counts), _lib.ptr(rec),
+                                     _lib.ptr(op._stats), _lib.ptr(ws), n, _lib.stream_ptr(dev))
+        _lib.check(rc, "fab_ais_chain_hmc_f32")
+        op._seen_first = True
+        op._seen_last = True
 
     def release_graphs(self):
         """Drop the captured CUDA graphs (and their persistent buffers).  With a process group, call

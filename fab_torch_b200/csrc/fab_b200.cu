@@ -187,6 +187,95 @@ int fab_flow_logprob_grad_f32(const fab_flow_desc* flow, const float* d_blob, co
     return FAB_OK;
 }
 
+/* ---- the whole single-rank HMC chain as one call (fab_ais_chain_f32) ------------------------- */
+namespace {
+struct ChainWs { size_t hmc, filter, part, prop, total; };
+ChainWs chain_ws(const fab_flow_desc& f, int64_t n, int n_outer, int use_rowtile) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    ChainWs w{};
+    size_t o = 0;
+    w.hmc = o; o += up((size_t)(use_rowtile ? fab_umma_workspace_bytes(&f, n) : fab_hmc_workspace_bytes(&f, n)));
+    w.filter = o; o += up((size_t)fab_filter_workspace_bytes(n, f.dim));
+    w.part = o; o += 256;
+    w.prop = o; if (n_outer > 1) o += up(2 * (size_t)n * (3 * f.dim + 2) * sizeof(float));
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+int64_t fab_ais_chain_workspace_bytes(const fab_flow_desc* flow, int64_t n, int32_t n_outer, int32_t use_rowtile) {
+    if (!flow_ok(flow) || n < 0 || n_outer < 1) return fail(FAB_E_INVALID, "fab_ais_chain_workspace_bytes: bad arguments");
+    if (use_rowtile && !fab_umma_supported(flow)) return fail(FAB_E_UNSUPPORTED, "row-tile engine does not cover this flow");
+    return (int64_t)chain_ws(*flow, n, n_outer, use_rowtile).total;
+}
+
+int fab_ais_chain_hmc_f32(const fab_flow_desc* flow, const float* d_blob, const void* d_ublob,
+                          const fab_target_desc* target, fab_hmc_state st, const fab_chain_hmc_args* a,
+                          const float* d_eps, fab_point pt, float* d_log_w, float* d_log_q0, uint8_t* d_valid,
+                          int32_t* d_counts, float* d_rec, float* d_stats, void* d_workspace, int64_t n,
+                          void* stream) {
+    if (!flow_ok(flow) || !a || !a->op_gammas || !a->w_gammas || !a->w_update || !a->d_mom || !a->d_exp ||
+        a->n_dist < 1 || a->n_outer < 1 || a->n_outer != st.n_outer || a->n_dist != st.n_dist || !d_counts || !d_rec ||
+        !d_workspace || n < 0 || (a->use_rowtile && !d_ublob))
+        return fail(FAB_E_INVALID, "fab_ais_chain_hmc_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    const int M = a->n_dist, d = flow->dim;
+    const ChainWs w = chain_ws(*flow, n, a->n_outer, a->use_rowtile);
+    char* ws = (char*)d_workspace;
+    float* part = (float*)(ws + w.part);
+    int e;
+    if ((e = fab_ais_init_f32(flow, d_blob, target, d_eps, a->w_gammas[1], 1, pt, d_log_w, d_log_q0, d_valid, n, stream))) return e;
+    if ((e = fab_nan_filter_f32(pt, d_log_w, d, n, nullptr, d_counts, ws + w.filter, stream))) return e;      // "chain init"
+    if (a->with_logging) {
+        if ((e = fab_ess_partial_f32(pt.d_log_p, pt.d_log_q, n, d_counts, part, stream))) return e;
+        if ((e = fab_ess_finalize_f32(part, 1, d_rec, stream))) return e;
+    }
+    fab_point prop[2] = {};
+    if (a->n_outer > 1) {
+        float* p = (float*)(ws + w.prop);
+        for (int s = 0; s < 2; ++s) {
+            prop[s].d_x = p; p += (size_t)n * d;
+            prop[s].d_grad_log_q = p; p += (size_t)n * d;
+            prop[s].d_grad_log_p = p; p += (size_t)n * d;
+            prop[s].d_log_q = p; p += n;
+            prop[s].d_log_p = p; p += n;
+        }
+    }
+    const fab_point none = {};
+    for (int j = 1; j <= M; ++j) {
+        fab_point prop_in = none;
+        for (int no = 0; no < a->n_outer; ++no) {
+            const bool last = no == a->n_outer - 1;
+            const bool upd = last && a->w_update[j] != 0;
+            fab_hmc_args h{};
+            h.i = j; h.outer = no; h.L = a->L; h.tune = a->tune;
+            h.target_p_accept = a->target_p_accept; h.max_grad = a->max_grad;
+            h.g = a->op_gammas[j];
+            h.update_log_w = upd ? 1 : 0;
+            h.g_w = upd ? a->w_gammas[j] : a->op_gammas[j];
+            h.g_next = upd ? a->w_gammas[j + 1] : a->op_gammas[j];
+            h.defer_stats = 0;
+            const fab_point prop_out = last ? none : prop[no & 1];
+            const float* mom = a->d_mom[j - 1] + (size_t)no * n * d;
+            const float* ex = a->d_exp[j - 1] + (size_t)no * n;
+            if (a->use_rowtile)
+                e = fab_hmc_step_umma_f32(flow, d_ublob, target, st, h, pt, prop_in, prop_out, d_log_w, mom, ex, d_counts,
+                                          d_stats, ws + w.hmc, n, stream);
+            else
+                e = fab_hmc_step_f32(flow, d_blob, target, st, h, pt, prop_in, prop_out, d_log_w, mom, ex, d_counts,
+                                     d_stats, ws + w.hmc, n, stream);
+            if (e) return e;
+            prop_in = prop_out;
+        }
+    }
+    if ((e = fab_nan_filter_f32(pt, d_log_w, d, n, d_counts, d_counts + 1, ws + w.filter, stream))) return e;  // "chain end"
+    if (a->with_logging) {
+        if ((e = fab_ess_partial_f32(d_log_w, nullptr, n, d_counts + 1, part, stream))) return e;
+        if ((e = fab_ess_finalize_f32(part, 1, d_rec + 3, stream))) return e;
+    }
+    return FAB_OK;
+}
+
 /* ---- parameter gradient of sum_i g_i log q(x_i) (param_grad.cuh) --------------------------------- */
 namespace {
 struct PgLayout {            // dense gradient buffer: [K layers][Ga | Gb | Gc | Gd] then [dloc | dlog_scale | sum g]

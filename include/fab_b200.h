@@ -302,6 +302,37 @@ int fab_buffer_adjust_f32(float* d_buf_log_w, float* d_buf_log_q, const int64_t*
                           void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * The whole chain in one call: AnnealedImportanceSampler.sample_and_log_weights (ais.py:53-87) with a
+ * HamiltonianMonteCarlo operator on ONE rank -- chain init (K1-K6, K11, K12), NaN/inf filter
+ * (:65, :190-213), ESS over the base weights (:68-71), the M fused transitions with the log-weight
+ * update (:74-75, :90-105), filter (:77), ESS and logsumexp of the final weights (:80-86).  Nothing
+ * but launches on `stream`: no allocation, no synchronisation (capturable in a CUDA graph).
+ * Host arrays: op_gammas / w_gammas [M+2] = gamma at beta_0..beta_{M+1} with the operator's and the
+ * sampler's (alpha, p_target) (they may differ, ais.py:94-98 vs hmc.py:188-191); w_update [M+1]:
+ * [j] != 0 iff beta_{j+1} != beta_j; d_mom / d_exp [M]: device pointers to the noise of transition
+ * j+1 ([n_outer, n, d] ~ N(0,1), [n_outer, n] ~ Exp(1)).
+ * Outputs: pt (live particles compacted to the front), d_log_w, d_log_q0 (forward-pass log q),
+ * d_counts[2] = live particles after chain init / at the chain end, d_rec[8]: [0..2] ESS,
+ * logsumexp, count of the base weights, [3..5] the same for the final weights (with_logging).
+ * Multi-rank chains stay with the caller (collectives between the launches).
+ * ------------------------------------------------------------------------------------- */
+typedef struct fab_chain_hmc_args {
+    int32_t n_dist, n_outer, L, tune, with_logging, use_rowtile;
+    float   target_p_accept, max_grad;
+    const fab_gamma* op_gammas;
+    const fab_gamma* w_gammas;
+    const uint8_t*   w_update;
+    const float* const* d_mom;
+    const float* const* d_exp;
+} fab_chain_hmc_args;
+int64_t fab_ais_chain_workspace_bytes(const fab_flow_desc* flow, int64_t n, int32_t n_outer, int32_t use_rowtile);
+int fab_ais_chain_hmc_f32(const fab_flow_desc* flow, const float* d_blob, const void* d_ublob /* row-tile images or NULL */,
+                          const fab_target_desc* target, fab_hmc_state st, const fab_chain_hmc_args* args,
+                          const float* d_eps, fab_point pt, float* d_log_w, float* d_log_q0, uint8_t* d_valid,
+                          int32_t* d_counts, float* d_rec, float* d_stats, void* d_workspace, int64_t n,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Parameter gradient of  sum_i g_i log q_theta(x_i)  -- the theta-gradient of the FAB loss
  * (fab/core.py:112-118: loss = -mean(softmax(log_w) * log q(x)); minibatch loop
  * fab/train_with_prioritised_buffer.py:158-186), replacing loss.backward() through

@@ -228,3 +228,40 @@ def test_cuda_graph_chain_equals_eager(op_kind):
         ais.set_next_noise(eps, a, b)
         outs.append(ais.sample_and_log_weights(B))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0].x, outs[1][0].x)
+
+
+@pytest.mark.parametrize("engine,dim,K,npd,B,n_outer", [("warp", 32, 4, 6, 300, 2), ("rowtile", 32, 3, 10, 1280, 1),
+                                                          ("warp", 6, 2, 5, 77, 1)])
+def test_c_chain_equals_python_loop(engine, dim, K, npd, B, n_outer, monkeypatch):
+    """`fab_ais_chain_hmc_f32` (the whole ais.py:53-87 loop as ONE C-ABI call) against the
+    launch-by-launch loop of `_run_chain` on the same seeds: bit-identical particles, log-weights,
+    logging record and tuner state, over several calls (tuner on), with NaN-producing particles in the
+    batch (filter) and for n_outer > 1 (the proposal carried into the next outer step)."""
+    monkeypatch.setenv("FAB_ENGINE", engine)
+    M = 5
+
+    def build():
+        _, _, fp = make_flows(dim, K, npd, last_std=0.02)
+        _, tp = make_manywell(dim)
+        op = fb.HamiltonianMonteCarlo(M, dim, fp.log_prob, tp.log_prob, alpha=2.0, p_target=False,
+                                      epsilon=0.1, L=3, n_outer=n_outer).cuda()
+        return fp, op, fb.AnnealedImportanceSampler(fp, tp.log_prob, op, p_target=False, alpha=2.0,
+                                                    n_intermediate_distributions=M)
+
+    (f_c, op_c, ais_c), (f_p, op_p, ais_p) = build(), build()
+    for step in range(4):
+        outs = []
+        for ais, flag in ((ais_c, "1"), (ais_p, "0")):
+            monkeypatch.setenv("FAB_C_CHAIN", flag)
+            torch.manual_seed(300 + step)
+            if step == 2:          # a few broken base samples: the chain-init filter drops them
+                eps = torch.randn(B, dim)
+                eps[3] = float("nan"); eps[B // 2] = float("inf")
+                ais.base_distribution._eps_override = eps.cuda()
+            outs.append(ais.sample_and_log_weights(B))
+        (pt_c, lw_c), (pt_p, lw_p) = outs
+        assert lw_c.shape == lw_p.shape and (step != 2 or lw_c.shape[0] < B)
+        assert torch.equal(lw_c, lw_p) and torch.equal(pt_c.x, pt_p.x) and torch.equal(pt_c.log_q, pt_p.log_q)
+        assert torch.equal(pt_c.grad_log_p, pt_p.grad_log_p)
+        assert ais_c.get_logging_info() == ais_p.get_logging_info()
+        assert torch.equal(op_c.epsilons, op_p.epsilons) and torch.equal(op_c.common_epsilon, op_p.common_epsilon)
