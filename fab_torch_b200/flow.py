@@ -159,6 +159,7 @@ class B200RealNVP(TrainableDistribution):
         self._ublob = None              # row-tile engine weight images (f16 hi/lo planes)
         self._ublob_key = None
         self._uws = None
+        self._plist = None              # cached parameter list (see _param_key)
         self._eps_override = None       # test hook: next sample uses this base noise
         # filled lazily: needs the .so
         self._desc_ready = False
@@ -173,7 +174,24 @@ class B200RealNVP(TrainableDistribution):
         return self._desc
 
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Changes whenever a parameter is updated in place (optimiser step, load_state_dict: version
+        counters) or moved (.to(): the cached list is dropped in `_apply`, and three storage addresses
+        are part of the key).  Walking `self.parameters()` and reading every data_ptr cost 0.3 ms per
+        call at config 2 -- twice per chain call -- so the list is cached and only versions are read."""
+        ps = self._plist
+        if ps is None:
+            ps = self._plist = list(self.parameters())
+        if not ps:
+            return ()
+        return (tuple(p._version for p in ps), ps[0].data_ptr(), ps[len(ps) // 2].data_ptr(), ps[-1].data_ptr())
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plist = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._plist = None
+        return super().load_state_dict(*args, **kwargs)
 
     def blob(self) -> torch.Tensor:
         """Packed fp32 weights on the parameters' device, rebuilt only when a parameter changed."""

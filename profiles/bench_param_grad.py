@@ -43,6 +43,20 @@ if __name__ == "__main__":
             flow.zero_grad(set_to_none=True)
             (-(w * flow.torch_log_prob(x)).mean()).backward()
 
+        # device time of the two kernel calls alone, and the per-optimiser-step repack of the weight blobs
+        lq, _, tape = flow.cuda_log_prob_tape(x, with_grad=False)
+        t_tape = timed(lambda: flow.cuda_log_prob_tape(x, with_grad=False))
+        t_pg = timed(lambda: flow.cuda_param_grad(tape, w))
+
+        def repack():
+            with torch.no_grad():
+                flow._nf_model.q0.loc.add_(0.0)          # version bump = "an optimiser step happened"
+            flow.blob()
+            if flow.rowtile_supported():
+                flow.umma_blob()
+        t_pack = timed(repack)
+        print(f"   kernels only: forward + tape {t_tape:.3f} ms, weight-gradient GEMMs + host chain rule {t_pg:.3f} ms; "
+              f"repack of the weight blob(s) after a parameter update {t_pack:.3f} ms")
         a, b = timed(step_cuda), timed(step_torch)
         step_cuda(); g1 = [p.grad.clone() for p in flow.parameters()]
         step_torch(); g2 = [p.grad.clone() for p in flow.parameters()]
