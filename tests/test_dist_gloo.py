@@ -57,6 +57,9 @@ def _worker(rank, world_size, port, out):
         assert float(stats[1]) == B
         assert abs(float(stats[0]) - (0.3 * B + sum(range(world_size)))) < 1e-4
         out[rank] = (float(ess), float(lse), float(stats[0]))
+        # the NVLink peer-memory exchange of the tuner statistics is for NCCL groups of CUDA devices:
+        # on a gloo / CPU group the operators must fall back to the all-reduce above
+        assert fdist.PeerExchange.create(group, torch.device("cpu")) is None
         # global systematic resample over ragged shards (rank 0 lost 3 particles to the NaN
         # filter): every rank must receive exactly its slice of the single-device answer.  The
         # ancestor routine is injected: on a GPU it is the integer kernel, here the oracle.

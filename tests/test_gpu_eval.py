@@ -79,3 +79,37 @@ def test_eval_info_chain():
               "flow_test_set_exact_mean_log_prob", "ais_abs_MSE_log_Z_estimate", "eval_ess_ais"):
         assert k in info and info[k] == info[k], k
     assert info["flow_eval_batch_size"] == 200 and 0.0 < info["eval_ess_ais"] <= 1.0
+
+
+def test_gmm_model_density_branch_on_device():
+    """gmm.py:71-99 with `log_q_fn`: the metrics that need the model density (test-set mean log q,
+    forward KL, ESS over p) through the CUDA flow / target kernels vs float64 torch on the SAME test
+    set (the reference draws a fresh test set on every access, so the set is pinned here)."""
+    from oracle.targets import OracleGMM, to_double
+    import copy
+    dim, n_mixes = 2, 6
+    torch.manual_seed(3)
+    tgt = fb.GMM(dim, n_mixes, 6.0, 0.5, true_expectation_estimation_n_samples=int(1e4))
+    torch.manual_seed(3)
+    orc = to_double(copy.deepcopy(OracleGMM(dim, n_mixes, 6.0, 0.5)))
+    assert torch.equal(orc.locs.float(), tgt.locs.cpu())
+    fo64, _, fp = make_flows(dim, 3, 10, seed=5)
+    g = torch.Generator().manual_seed(8)
+    test_set = torch.randn(1000, dim, generator=g) * 3.0
+    original = fb.GMM.__dict__["test_set"]
+    fb.GMM.test_set = property(lambda self: test_set.cuda())              # pinned for this test
+    try:
+        x = torch.randn(400, dim, generator=g).cuda()
+        log_w = torch.randn(400, generator=g).cuda()
+        tgt._true_expectation = torch.tensor(1.0, device="cuda")
+        got = tgt.performance_metrics(x, log_w, lambda t: fp.log_prob(t).detach())
+    finally:
+        fb.GMM.test_set = original
+    lq = fo64.log_prob(test_set.double()).detach()
+    lp = orc.log_prob(test_set.double())
+    ratio = lp - lq
+    want = dict(test_set_mean_log_prob=lq.mean().item(), kl_forward=ratio.mean().item(),
+                ess_over_p=(1 / torch.exp(ratio).mean()).item())
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 2e-5 * (1.0 + abs(v)), (k, got[k], v)
+    assert set(got) == {"test_set_mean_log_prob", "bias_normed", "bias_no_correction", "ess_over_p", "kl_forward"}
