@@ -430,7 +430,8 @@ def run_gpu_arm(args):
                     warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=config_block(cfg, world),
-                    engine=dict(hmc_step="row-tile tcgen05 (f16 hi/lo operands, fp32 accumulate)" if rowtile
+                    engine=dict(hmc_step="row-tile tcgen05 (f16 hi/lo operands = 22 significant bits of every fp32 weight "
+                                         "and activation, fp32 accumulate)" if rowtile
                                 else "warp-level mma.sync 3xTF32 (weights rounded to 22 bits)",
                                 cuda_graph=bool(ais.use_cuda_graph),
                                 tuner_exchange=("none (one rank)" if world == 1 else
