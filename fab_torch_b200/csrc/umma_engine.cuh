@@ -463,29 +463,35 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
         for (int e = e0; e < e1; ++e) {
             const UOp& o = L.ops[ROLE][e];
             const uint32_t f = o.flags;
+            // the entry's fields are read BEFORE the waits: the constant-bank latency then overlaps the wait
+            // instead of sitting between the barrier and the first MMA of every round trip
+            const uint32_t o_a = o.a, o_b = o.b, al = o.a_lo, kstr = o.kstr, o_d0 = o.d0, o_d1 = o.d1, id0 = o.idesc0,
+                           id1 = o.idesc1, nbh = o.nbh, o_count = o.count, o_it = o.it_rel;
+            // the weight stage first (it is prefetched: the ~80-cycle poll of a complete barrier then
+            // runs while the operands are still being written), then the operand barriers
+            if (f & UOP_NEWSTAGE) {
+                const uint32_t it = it_base + o_it;
+                slot = it % UE_NSTAGE;
+                UE_T0(); umma::mbar_wait_cluster(B.full + slot, (it / UE_NSTAGE) & 1); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
+                sb4 = ring4 + slot * (UE_STAGE_BYTES >> 4);
+            }
             if (f & UOP_WAIT_A0) {
                 UE_T0(); umma::mbar_wait_cluster(B.aready, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
             }
             if (f & UOP_WAIT_A1) {
                 UE_T0(); umma::mbar_wait_cluster(B.aready + 1, gi & 1); UE_ACC(2, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
             }
-            if (f & UOP_NEWSTAGE) {
-                const uint32_t it = it_base + o.it_rel;
-                slot = it % UE_NSTAGE;
-                UE_T0(); umma::mbar_wait_cluster(B.full + slot, (it / UE_NSTAGE) & 1); UE_ACC(3, blockIdx.x == 0 && (threadIdx.x & 31) == 0);
-                sb4 = ring4 + slot * (UE_STAGE_BYTES >> 4);
-            }
             if (f & (UOP_WAIT_A0 | UOP_WAIT_A1 | UOP_NEWSTAGE)) umma::tc_fence_after();
             {
                 UE_T0();
-                uint32_t ah = sbase4 + o.a, bk = sb4 + o.b, acc = (f & UOP_ACC) ? 1u : 0u;
-                const uint32_t al = o.a_lo, kstr = o.kstr, d0 = tmem + o.d0, d1 = tmem + o.d1, id0 = o.idesc0, id1 = o.idesc1, nbh = o.nbh;
+                uint32_t ah = sbase4 + o_a, bk = sb4 + o_b, acc = (f & UOP_ACC) ? 1u : 0u;
+                const uint32_t d0 = tmem + o_d0, d1 = tmem + o_d1;
 #ifdef UE_X_NOMMA
                 if (false) {
 #else
                 if (f & UOP_WIDE) {
 #endif
-                    for (uint32_t n = o.count; n > 0; --n) {
+                    for (uint32_t n = o_count; n > 0; --n) {
                         umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id0, acc, lead);           // cross  = lo * hi
                         umma::mma_ss2_pred(d1, desc(ah), desc(bk + nbh), id0, 1u, lead);           // cross += hi * lo
                         umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // main   = hi * hi
@@ -496,7 +502,7 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
 #else
                 } else {
 #endif
-                    for (uint32_t n = o.count; n > 0; --n) {
+                    for (uint32_t n = o_count; n > 0; --n) {
                         umma::mma_ss2_pred(d0, desc(ah), desc(bk), id0, acc, lead);                // [hi*hi | hi*lo]
                         umma::mma_ss2_pred(d1, desc(ah + al), desc(bk), id1, 1u, lead);            // += lo*hi
                         ah += 128; bk += kstr; acc = 1u;
@@ -560,11 +566,10 @@ __device__ __forceinline__ void ue_row_sum2(const ULayout& L, UCw& c, float& a, 
     b = ((e2[c.r] + e2[UE_ROWS + c.r]) + e2[2 * UE_ROWS + c.r]) + e2[3 * UE_ROWS + c.r];
 }
 // Sum of squares of a hidden operand row, handed from the epilogue that wrote the operand to the
-// epilogue of the GEMM that consumes it.  The consumer runs after accumulators that every writer's
-// operand-ready arrival precedes, so the values are long in place; the CTA barrier in ue_ssq_get makes
-// that ordering explicit (all compute threads have just passed the same accumulator wait, it costs
-// ~0.5 % of a layer) and two alternating buffers keep a fast thread's next hand-off away from a slow
-// thread's read.
+// epilogue of the GEMM that consumes it.  Every compute thread writes its part at the end of its
+// epilogue; the reader first passes a CTA barrier of the 256 compute threads (so all four parts of
+// its row are in place) -- this happens while the consuming GEMM's MMAs run, before the accumulator
+// wait.  Two alternating buffers keep a fast thread's next hand-off away from a slow thread's read.
 __device__ __forceinline__ void ue_ssq_put(const ULayout& L, UCw& c, float v) {
     reinterpret_cast<float*>(ue_smem + L.s_ssq)[(c.nq & 1) * (4 * UE_ROWS) + c.q * UE_ROWS + c.r] = v;
 }
@@ -719,8 +724,8 @@ __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uin
 #undef UE_BJ
 }
 // Both blocks of a wide GEMM, with the barrier protocol around them.  bound_fn(): upper bound of the
-// row maximum of the result (evaluated after the first accumulator wait: it may read the hand-off of
-// the previous epilogue); cf: un-scale of the accumulators (operand scale x weight scale); returns the
+// row maximum of the result (evaluated before the first accumulator wait; it may read the hand-off of
+// the previous epilogue, which ue_ssq_get orders with a CTA barrier); cf: un-scale of the accumulators (operand scale x weight scale); returns the
 // new operand's inverse scale and (ssq_out) the thread's part of its squared row norm in UNSCALED units.
 // between(blk): work after the wait for block blk (type 0: the v columns behind block c.g).
 template <bool FWD, bool BIASED, int NC8, class FB, class F>
@@ -729,13 +734,15 @@ __device__ __forceinline__ float ue_epi_wide(const ULayout& L, UCw& c, const UTy
     const uint32_t t0 = c.tmem + c.tl + t.dcol + c.g * (L.WQ / 2);      // the thread's first column of block 0 (main)
     float ssq = 0.f;
     if (FWD) { mask[0] = 0u; mask[1] = 0u; mask[2] = 0u; }
-    ue_wait_acc(L, c, 0);
-    ++c.n0;
+    // the operand scale is computed BEFORE the accumulator wait (it depends on the previous epilogue's
+    // hand-off at most, never on this GEMM): off the critical path of the round trip
     float s, inv_s;
     ue_scale_of<BIASED>(bound_fn(), s, inv_s);
     // un-scale, compensate and re-scale with one factor: s and cf are powers of two, (1 + dl) is a
     // few ulp for these long chains
     const float sc = cf * s * (1.0f + dl);
+    ue_wait_acc(L, c, 0);
+    ++c.n0;
     if (BIASED && c.q == 0) ue_store_one(ue_smem + L.s_h, L.W / 8, c.r, s);
     between(0);
     ue_epi_block<FWD, NC8, 0>(L, c, t0, t0 + t.nbh, sc, mask, ssq);
@@ -836,7 +843,7 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
                     sv[i] = __float_as_uint(y2);
                     sv[UE_DQ + i] = __float_as_uint(es);
                 }
-                if (GRAD) { umma::tmem_st16(tl + UE_ACC_COLS + 16 * k, sv); umma::tmem_st_wait(); }
+                if (GRAD) umma::tmem_st16(tl + UE_ACC_COLS + 16 * k, sv);       // (completion: one wait before the gradient sweep)
             } else {
 #pragma unroll
                 for (int i = 0; i < UE_DQ; ++i) zc[i] = vreg[i];
@@ -873,6 +880,7 @@ __device__ __forceinline__ float ue_flow_eval(const ULayout& L, UCw& c, const fl
     for (int k = 0; k < L.K; ++k) logs += __ldg(scal + k * UE_SCAL + 7);
     const float lq = logs + (-0.5f * (float)L.d * 1.8378770664093453f - (gpart + sacc));
     if (!GRAD) return lq;
+    umma::tmem_st_wait();           // the saved (y2, exp(-scale)) of all layers are in tensor memory
     // ---- input-gradient sweep ---------------------------------------------------------------------
     uint8_t* const pp = ue_smem + L.s_par;
     uint8_t* const gp = ue_smem + L.s_gv;
