@@ -231,9 +231,10 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
                         // block 1 overwrites accumulators that the previous group's second epilogue reads: it waits
                         // for both operand halves before its first MMA; block 0 / narrow types wait for the second
                         // half only where they reach it
+                        // (waiting for the second half implies the first: every warp arrives on A0 before A1)
                         if (first[r]) {
-                            f |= UOP_WAIT_A0;
                             if (!t.hin || g == 1) { f |= UOP_WAIT_A1; a1[r] = true; }
+                            else f |= UOP_WAIT_A0;
                             first[r] = false;
                         }
                         if (!a1[r] && ja >= t.kfirst) { f |= UOP_WAIT_A1; a1[r] = true; }
@@ -258,7 +259,7 @@ __host__ inline ULayout make_ulayout(int d, int W, int K) {
             // D1 phase always come from the two issuers)
             UOp& o = L.ops[1][no[1]++];
             o = UOp{};
-            o.flags = UOP_WAIT_A0 | UOP_WAIT_A1 | UOP_D1;
+            o.flags = UOP_WAIT_A1 | UOP_D1;
         }
     };
     group(0, 0); group(1, 1); group(2, 2);
