@@ -56,8 +56,8 @@
 #define UE_ROWS 64
 #define UE_THREADS 352
 #define UE_CTHREADS 256
-#define UE_STAGE_BYTES 22528      // two k-steps of the widest operand (352 rows x 32 bytes each)
-#define UE_NSTAGE 4
+#define UE_STAGE_BYTES 30720      // six k-steps of a W x W column block (160 rows x 32 bytes each); 3 x 30 KB measured best (4 x 22.5 KB: 0.682 ms, 2 x 45 KB: 0.702)
+#define UE_NSTAGE 3
 #define UE_ACC_COLS 352          // accumulator columns; [352, 512) hold the saved coupling state
 #define UE_DQ 8                  // columns of a d-wide vector per thread (d = 32)
 #define UE_TRUNC_PER_ACC 1.67e-8f
