@@ -598,6 +598,32 @@ __device__ __forceinline__ void ue_scale_of(float m, float& s, float& inv_s) {
     s = __uint_as_float((uint32_t)(es + 127) << 23);
     inv_s = __uint_as_float((uint32_t)(127 - es) << 23);
 }
+// packed fp32 pairs (sm_100: add / mul / fma .f32x2 do two lanes per instruction; the epilogues are
+// issue-bound).  -DUE_NO_F32X2 keeps the scalar forms.
+__device__ __forceinline__ void ue_add2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+#ifdef UE_NO_F32X2
+    x0 = a0 + b0; x1 = a1 + b1;
+#else
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+#endif
+}
+__device__ __forceinline__ void ue_mul2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+#ifdef UE_NO_F32X2
+    x0 = a0 * b0; x1 = a1 * b1;
+#else
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+#endif
+}
+__device__ __forceinline__ void ue_fma2(float& x0, float& x1, float a0, float a1, float b0, float b1, float c0, float c1) {
+#ifdef UE_NO_F32X2
+    x0 = fmaf(a0, b0, c0); x1 = fmaf(a1, b1, c1);
+#else
+    asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\tfma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+#endif
+}
 // split eight scaled values into f16 hi / lo and store them as one 16-byte k-chunk of row r
 __device__ __forceinline__ void ue_store_chunk(uint8_t* hi_plane, int a_lo, int chunk, int r, const float (&v)[8]) {
     uint32_t hw[4], lw[4];
@@ -605,7 +631,9 @@ __device__ __forceinline__ void ue_store_chunk(uint8_t* hi_plane, int a_lo, int 
     for (int i = 0; i < 4; ++i) {
         const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
         const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        float l0, l1;
+        ue_fma2(l0, l1, hf.x, hf.y, -1.0f, -1.0f, v[2 * i], v[2 * i + 1]);       // v - hi (exact: a product with -1)
+        const __half2 ll = __floats2half2_rn(l0, l1);
         hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
         lw[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
@@ -681,6 +709,7 @@ __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uin
 #endif
     uint8_t* hp = ue_smem + L.s_h;
     const int chunk0 = ((2 * G + c.h) * L.WQ) / 8 + c.g * NC8;
+    float ssq2 = 0.f;                  // second lane of the packed sum of squares
     // software-pipelined over the chunks: the loads of chunk j+1 are in flight while chunk j is scaled /
     // split / stored (tcgen05.wait::ld waits for everything outstanding, so the next loads are issued
     // right AFTER the wait)
@@ -712,17 +741,26 @@ __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uin
         uint32_t bits = 0;
         float hv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float v = (__uint_as_float(UE_AJ(j)[i]) + __uint_as_float(UE_BJ(j)[i])) * sc;
-            if (FWD) { const bool on = v > 0.f; bits |= (on ? 1u : 0u) << i; hv[i] = on ? v : 0.f; }
-            else hv[i] = ((mw >> i) & 1u) ? v : 0.f;
-            ssq = fmaf(hv[i], hv[i], ssq);
+        for (int i = 0; i < 8; i += 2) {
+            float v0, v1;
+            ue_add2(v0, v1, __uint_as_float(UE_AJ(j)[i]), __uint_as_float(UE_AJ(j)[i + 1]),
+                    __uint_as_float(UE_BJ(j)[i]), __uint_as_float(UE_BJ(j)[i + 1]));
+            ue_mul2(v0, v1, v0, v1, sc, sc);
+            if (FWD) {
+                const bool on0 = v0 > 0.f, on1 = v1 > 0.f;
+                bits |= ((on0 ? 1u : 0u) << i) | ((on1 ? 1u : 0u) << (i + 1));
+                hv[i] = on0 ? v0 : 0.f; hv[i + 1] = on1 ? v1 : 0.f;
+            } else {
+                hv[i] = ((mw >> i) & 1u) ? v0 : 0.f; hv[i + 1] = ((mw >> (i + 1)) & 1u) ? v1 : 0.f;
+            }
+            ue_fma2(ssq, ssq2, hv[i], hv[i + 1], hv[i], hv[i + 1], ssq, ssq2);
         }
         if (FWD) mask[bit0 >> 5] |= bits << (bit0 & 31);
         ue_store_chunk(hp, L.hplane, chunk0 + j, c.r, hv);
     }
 #undef UE_AJ
 #undef UE_BJ
+    ssq += ssq2;
 }
 // Both blocks of a wide GEMM, with the barrier protocol around them.  bound_fn(): upper bound of the
 // row maximum of the result (evaluated before the first accumulator wait; it may read the hand-off of
