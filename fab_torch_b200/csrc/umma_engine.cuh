@@ -20,14 +20,18 @@
 //     element within 2^-9 of the largest representable scaled value and 2^-25 absolute below that,
 //     far inside fp32 -- and it removes both the extra pass over the accumulators and the
 //     dependency of one column block's epilogue on the other block.
-//   * MMA / epilogue overlap, in place: a wide GEMM is issued block by block (two blocks of N/2
-//     output columns), block 1 with its k loop split in halves:
-//         (blk0, k-half 0 + bias) | wait A1 | (blk0, k-half 1) (blk1, k-half 0 + bias) -> D0 | (blk1, k-half 1) -> D1
-//     D0 says "block 0 is complete AND nobody reads the first half of the A operand any more", so
-//     the epilogue of block 0 -- which overwrites exactly that half of the operand buffer with the
-//     next GEMM's operand -- runs under the MMAs of (blk1, k-half 1); the epilogue of block 1 runs
-//     under (blk0, k-half 0) of the NEXT GEMM, which the issuer starts as soon as block 0's
-//     columns have been written (A0).  All 8 compute warps work on each block.
+//   * MMA / epilogue overlap, in place: a wide GEMM is issued as two column blocks of N/2 outputs, each
+//     by its own issuer warp, with the k loop in halves (the operand of the NEXT GEMM is written half
+//     by half into the buffer this GEMM still reads):
+//         issuer 0:  wait A0 | (blk0, k-half 0 + bias) | wait A1 | (blk0, k-half 1)        -> D0, D1
+//         issuer 1:  wait A1 | (blk1, k-half 0 + bias) -> D0 | (blk1, k-half 1)            -> D1
+//     A0 / A1 = "operand half 0 / 1 is written" (16 warp arrivals each), D0 / D1 = accumulator barriers
+//     (one commit per issuer each).  D0 says "block 0 is complete AND nobody reads the first half of
+//     the A operand any more", so the epilogue of block 0 -- which overwrites exactly that half with
+//     the next GEMM's operand -- can run under the tail of block 1's MMAs; the epilogue of block 1
+//     runs under (blk0, k-half 0) of the NEXT GEMM, which issuer 0 starts as soon as block 0's
+//     columns have been written (A0).  Block 1's accumulators are still being read by that second
+//     epilogue, hence issuer 1 waits for A1.  All 8 compute warps work on each block.
 //   * Thread (row r, lane half h, warp half u) owns, in every block, columns [u WQ/2, (u+1) WQ/2)
 //     of lane half h, and columns 8 (2u+h) .. +7 of every d-wide vector for the whole kernel: the
 //     running latent, the momentum and the gradients live in its registers; only MMA operands pass
@@ -487,7 +491,7 @@ __device__ void ue_mma(const ULayout& L, uint32_t tmem, int n_evals, bool grad) 
                 UE_T0();
                 uint32_t ah = sbase4 + o_a, bk = sb4 + o_b, acc = (f & UOP_ACC) ? 1u : 0u;
                 const uint32_t d0 = tmem + o_d0, d1 = tmem + o_d1;
-#ifdef UE_X_NOMMA
+#ifdef UE_X_NOMMA      // (timing experiments of profiles/r02_rowtile_experiments.md: the kernel without its MMAs)
                 if (false) {
 #else
                 if (f & UOP_WIDE) {
@@ -704,7 +708,7 @@ __device__ __forceinline__ void ue_acc8(uint32_t ta_main, uint32_t ta_cross, flo
 template <bool FWD, int NC8, int G>
 __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uint32_t ta_main, uint32_t ta_cross, float sc,
                                              uint32_t (&mask)[3], float& ssq) {
-#ifdef UE_X_NOEPI
+#ifdef UE_X_NOEPI      // (timing experiments of profiles/r02_rowtile_experiments.md: the kernel without its wide epilogues)
     return;
 #endif
     uint8_t* hp = ue_smem + L.s_h;
@@ -712,30 +716,17 @@ __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uin
     float ssq2 = 0.f;                  // second lane of the packed sum of squares
     // software-pipelined over the chunks: the loads of chunk j+1 are in flight while chunk j is scaled /
     // split / stored (tcgen05.wait::ld waits for everything outstanding, so the next loads are issued
-    // right AFTER the wait)
-#ifdef UE_LOADS_UPFRONT
-    uint32_t a[NC8][8], b[NC8][8];
-#pragma unroll
-    for (int j = 0; j < NC8; ++j) { umma::tmem_ld8(ta_main + 8 * j, a[j]); umma::tmem_ld8(ta_cross + 8 * j, b[j]); }
-    umma::tmem_ld_wait();
-#define UE_AJ(j) a[j]
-#define UE_BJ(j) b[j]
-#else
+    // right AFTER the wait).  Issuing all loads of the block up front was measured: no difference.
     uint32_t a[2][8], b[2][8];
     umma::tmem_ld8(ta_main, a[0]);
     umma::tmem_ld8(ta_cross, b[0]);
-#define UE_AJ(j) a[(j) & 1]
-#define UE_BJ(j) b[(j) & 1]
-#endif
 #pragma unroll
     for (int j = 0; j < NC8; ++j) {
-#ifndef UE_LOADS_UPFRONT
         umma::tmem_ld_wait();
         if (j + 1 < NC8) {
             umma::tmem_ld8(ta_main + 8 * (j + 1), a[(j + 1) & 1]);
             umma::tmem_ld8(ta_cross + 8 * (j + 1), b[(j + 1) & 1]);
         }
-#endif
         const int bit0 = (G * NC8 + j) * 8;
         const uint32_t mw = FWD ? 0u : mask[bit0 >> 5] >> (bit0 & 31);
         uint32_t bits = 0;
@@ -743,8 +734,8 @@ __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uin
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
             float v0, v1;
-            ue_add2(v0, v1, __uint_as_float(UE_AJ(j)[i]), __uint_as_float(UE_AJ(j)[i + 1]),
-                    __uint_as_float(UE_BJ(j)[i]), __uint_as_float(UE_BJ(j)[i + 1]));
+            ue_add2(v0, v1, __uint_as_float(a[j & 1][i]), __uint_as_float(a[j & 1][i + 1]),
+                    __uint_as_float(b[j & 1][i]), __uint_as_float(b[j & 1][i + 1]));
             ue_mul2(v0, v1, v0, v1, sc, sc);
             if (FWD) {
                 const bool on0 = v0 > 0.f, on1 = v1 > 0.f;
@@ -758,8 +749,6 @@ __device__ __forceinline__ void ue_epi_block(const ULayout& L, const UCw& c, uin
         if (FWD) mask[bit0 >> 5] |= bits << (bit0 & 31);
         ue_store_chunk(hp, L.hplane, chunk0 + j, c.r, hv);
     }
-#undef UE_AJ
-#undef UE_BJ
     ssq += ssq2;
 }
 // Both blocks of a wide GEMM, with the barrier protocol around them.  bound_fn(): upper bound of the
