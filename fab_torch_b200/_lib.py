@@ -136,8 +136,12 @@ SIGNATURES = {
 def engine_choice() -> str:
     """FAB_ENGINE = auto (default) | rowtile | warp.  `auto` takes the row-tile (tcgen05) engine
     when the flow shape is covered and the batch holds at least FAB_ROWTILE_MIN_N particles
-    (default 1024: below that the 128-row tiles leave most SMs idle and the warp-level engine,
-    which spreads <= 16 particles per SM, is faster)."""
+    (default 1024).  Both engines are latency-bound per tile -- 0.67 vs 1.45 ms per fused HMC launch
+    at config 2 for every batch from 64 to 2 048 particles (profiles/engine_crossover.py) -- so the
+    row-tile engine is the faster one at any size; the default keeps small batches on the warp-level
+    engine because the reference-generated golden fixtures (64 particles, tests/test_gpu_golden.py)
+    are held to 4x the CPU-fp32 error per teacher-forced step and one chaotic log p row of the
+    row-tile engine sits at 4.4x."""
     return os.environ.get("FAB_ENGINE", "auto")
 
 
