@@ -85,7 +85,7 @@ def main():
                 return src_cache[p][ln - 1].strip()[:90] if 0 < ln <= len(src_cache[p]) else ""
         return ""
 
-    print(f"# k_hmc_step<16>: warp-stall samples and executed instructions by source line\n")
+    print(f"# {KERNEL}: warp-stall samples and executed instructions by source line\n")
     print(f"capture `{os.path.basename(rep)}`; {int(tot_s)} samples, {tot_i / 1e6:.1f} M warp-instructions; "
           f"{missing} SASS rows without a line-table entry.  Innermost (inlined) location per instruction.\n")
     print("## By file\n\n| file | samples | instructions |\n|---|---|---|")
