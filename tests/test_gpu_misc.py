@@ -246,3 +246,40 @@ def test_resample_without_any_finite_weight_raises():
     lw = torch.full((64,), float("nan"), device="cuda")
     with pytest.raises(ValueError):
         systematic_ancestors(lw, 7)
+
+
+def test_hmc_finish_over_peer_buffers_single_rank():
+    """`fab_hmc_finish_peer_f32` (tuner statistics summed over peer-mapped exchange buffers) with a
+    world of ONE: the rank stores its triple into its own buffer, reads it back and must apply exactly
+    the update `fab_hmc_finish_f32` applies -- over more exchanges than the ring has slots (sequence
+    counter, slot reuse).  The multi-rank path is exercised by `bench.py --gpus N` / tests/multi_gpu_check.py."""
+    from fab_torch_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+
+    def mk():
+        _, _, fp = __import__("helpers").make_flows(4, 1, 2)
+        tp = fb.ManyWellEnergy(4)
+        return fb.HamiltonianMonteCarlo(3, 4, fp.log_prob, tp.log_prob, alpha=2.0, p_target=False,
+                                        epsilon=0.2, L=2).cuda()
+    op_a, op_b = mk(), mk()
+    nbytes = int(L.fab_hmc_peer_buffer_bytes(1))
+    assert nbytes == 4 * 1 * 8 * 4
+    buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=dev)
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=dev)
+    seq = torch.zeros(1, dtype=torch.int32, device=dev)
+    g = _lib.Gamma(0.5, 0.5, 0.5, 1.0)
+    gen = torch.Generator().manual_seed(4)
+    for k in range(9):                      # > FAB_PEER_RING exchanges
+        i = 1 + k % 3
+        stats = torch.tensor([float(torch.rand((), generator=gen)) * 100, 128.0,
+                              float(torch.rand((), generator=gen)) * 10, 0.0], device=dev)
+        args = _lib.HmcArgs(i, 0, 2, 1, 0.65, 1000.0, g, 0, g, g, 1)
+        _lib.check(L.fab_hmc_finish_f32(op_a._state(), args, _lib.ptr(stats), _lib.stream_ptr(dev)), "finish")
+        _lib.check(L.fab_hmc_finish_peer_f32(op_b._state(), args, _lib.ptr(stats), _lib.ptr(ptrs), 1, 0,
+                                             _lib.ptr(seq), _lib.stream_ptr(dev)), "finish_peer")
+    torch.cuda.synchronize()
+    assert int(seq.item()) == 9
+    assert torch.equal(op_a.epsilons, op_b.epsilons) and torch.equal(op_a.common_epsilon, op_b.common_epsilon)
+    assert torch.equal(op_a._log, op_b._log)
+    assert not torch.equal(op_a.epsilons, mk().epsilons)          # the tuner did move
