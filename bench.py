@@ -425,7 +425,9 @@ def run_gpu_arm(args):
                          "required; pipe_frac is vs the ceiling of the engine and of the SMs this batch can "
                          "occupy (DESIGN.md 4: the chain is sequential per particle and 2048 particles are 16 "
                          "row tiles of 128)")
-        launches_per_step = 1 + 3 + 2 + cfg["M"] * cfg["n_outer"] * (2 if world > 1 else 1) + 3 + 2
+        # chain init (1 fused launch on the warp engine; sample + row-tile log q / gradient + target + tail on the
+        # row-tile engine), filter 3, ESS 2, M transitions (+ the tuner exchange launch at N > 1), filter 3, ESS 2
+        launches_per_step = (4 if rowtile else 1) + 3 + 2 + cfg["M"] * cfg["n_outer"] * (2 if world > 1 else 1) + 3 + 2
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",

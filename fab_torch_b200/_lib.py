@@ -127,6 +127,8 @@ SIGNATURES = {
     "fab_umma_pack_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, _P]),
     "fab_umma_workspace_bytes": (C.c_int64, [C.POINTER(FlowDesc), C.c_int64]),
     "fab_flow_logprob_grad_umma_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "fab_ais_init_umma_f32": (C.c_int, [C.POINTER(FlowDesc), _P, _P, C.POINTER(TargetDesc), _P, Gamma, PointPtrs,
+                                        _P, _P, _P, _P, C.c_int64, _P]),
     "fab_hmc_step_umma_f32": (C.c_int, [C.POINTER(FlowDesc), _P, C.POINTER(TargetDesc), HmcState,
                                         HmcArgs, PointPtrs, PointPtrs, PointPtrs, _P, _P, _P, _P, _P,
                                         _P, C.c_int64, _P]),

@@ -158,11 +158,21 @@ class AnnealedImportanceSampler:
             self._run_chain_c(pt, log_w, log_q0, valid, counts, rec, eps, chain_noise, logging)
             return pt, log_w, counts, rec
         g1 = make_gamma(self.B_space[1], self.alpha, self.p_target)
-        rc = L.fab_ais_init_f32(flow.desc(), _lib.ptr(flow.blob()), target.target_desc(dev),
-                                _lib.ptr(eps.contiguous()), g1, 1 if with_grad else 0,
-                                _lib.point_ptrs(pt), _lib.ptr(log_w), _lib.ptr(log_q0),
-                                _lib.ptr(valid), n, _lib.stream_ptr(dev))
-        _lib.check(rc, "fab_ais_init_f32")
+        tdesc = target.target_desc(dev)
+        if with_grad and tdesc.kind == _lib.FAB_TARGET_MANYWELL and flow.use_rowtile(n):
+            # same engine choice as the transitions (and as fab_ais_chain_hmc_f32): inverse-pass log q and
+            # its gradient on the row-tile engine
+            ws = op._workspace(int(L.fab_umma_workspace_bytes(flow.desc(), n)), dev)
+            rc = L.fab_ais_init_umma_f32(flow.desc(), _lib.ptr(flow.blob()), _lib.ptr(flow.umma_blob()), tdesc,
+                                         _lib.ptr(eps.contiguous()), g1, _lib.point_ptrs(pt), _lib.ptr(log_w),
+                                         _lib.ptr(log_q0), _lib.ptr(valid), _lib.ptr(ws), n, _lib.stream_ptr(dev))
+            _lib.check(rc, "fab_ais_init_umma_f32")
+        else:
+            rc = L.fab_ais_init_f32(flow.desc(), _lib.ptr(flow.blob()), tdesc,
+                                    _lib.ptr(eps.contiguous()), g1, 1 if with_grad else 0,
+                                    _lib.point_ptrs(pt), _lib.ptr(log_w), _lib.ptr(log_q0),
+                                    _lib.ptr(valid), n, _lib.stream_ptr(dev))
+            _lib.check(rc, "fab_ais_init_f32")
         self._filter(pt, log_w, None, counts[0:1])                 # "chain init"
         if logging:
             self._ess(pt.log_p, pt.log_q, counts[0:1], rec[0:3])   # ESS over base weights

@@ -224,7 +224,12 @@ int fab_ais_chain_hmc_f32(const fab_flow_desc* flow, const float* d_blob, const 
     char* ws = (char*)d_workspace;
     float* part = (float*)(ws + w.part);
     int e;
-    if ((e = fab_ais_init_f32(flow, d_blob, target, d_eps, a->w_gammas[1], 1, pt, d_log_w, d_log_q0, d_valid, n, stream))) return e;
+    if (a->use_rowtile)
+        e = fab_ais_init_umma_f32(flow, d_blob, d_ublob, target, d_eps, a->w_gammas[1], pt, d_log_w, d_log_q0, d_valid,
+                                  ws + w.hmc, n, stream);
+    else
+        e = fab_ais_init_f32(flow, d_blob, target, d_eps, a->w_gammas[1], 1, pt, d_log_w, d_log_q0, d_valid, n, stream);
+    if (e) return e;
     if ((e = fab_nan_filter_f32(pt, d_log_w, d, n, nullptr, d_counts, ws + w.filter, stream))) return e;      // "chain init"
     if (a->with_logging) {
         if ((e = fab_ess_partial_f32(pt.d_log_p, pt.d_log_q, n, d_counts, part, stream))) return e;

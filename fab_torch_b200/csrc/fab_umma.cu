@@ -114,6 +114,41 @@ int fab_flow_logprob_grad_umma_f32(const fab_flow_desc* flow, const void* d_ublo
     return fab_fail(FAB_E_UNSUPPORTED, "row-tile engine: unsupported width");
 }
 
+/* Chain initialisation (ais.py:56-65) around the row-tile engine: the flow sample on the tile engine
+ * (eps -> x, forward-pass log q), log q and its input-gradient re-evaluated by the inverse pass on the
+ * row-tile engine (create_point(with_grad=True)), the streaming target kernel, and
+ * a one-line tail for the first log-weight and the validity flags.  Same contract as fab_ais_init_f32
+ * with with_grad = 1; d_log_q0 is required. */
+__global__ void k_ais_init_tail(fab_gamma g1, const float* __restrict__ lq, const float* __restrict__ lp,
+                                const float* __restrict__ lq0, float* __restrict__ log_w, uint8_t* __restrict__ valid,
+                                long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float q = lq[i], p = lp[i];
+    log_w[i] = __fsub_rn(gamma_of(g1, q, p), lq0[i]);
+    valid[i] = (fab_isfinite(q) && fab_isfinite(p)) ? 1 : 0;
+}
+
+int fab_ais_init_umma_f32(const fab_flow_desc* flow, const float* d_blob, const void* d_ublob,
+                          const fab_target_desc* target, const float* d_eps, fab_gamma g1, fab_point out,
+                          float* d_log_w, float* d_log_q0, uint8_t* d_valid, void* d_workspace, int64_t n,
+                          void* stream) {
+    if (!umma_flow_ok(flow) || !fab_target_ok(target) || target->dim != flow->dim || !d_blob || !d_ublob || !d_eps ||
+        !out.d_x || !out.d_log_q || !out.d_log_p || !out.d_grad_log_q || !out.d_grad_log_p || !d_log_w || !d_log_q0 ||
+        !d_valid || !d_workspace || n < 0)
+        return fab_fail(FAB_E_INVALID, "fab_ais_init_umma_f32: bad arguments");
+    if (n == 0) return FAB_OK;
+    int e;
+    if ((e = fab_flow_sample_f32(flow, d_blob, d_eps, out.d_x, d_log_q0, n, stream))) return e;
+    if ((e = fab_flow_logprob_grad_umma_f32(flow, d_ublob, out.d_x, out.d_log_q, out.d_grad_log_q, d_workspace, n, stream)))
+        return e;
+    if ((e = fab_target_logprob_grad_f32(target, out.d_x, out.d_log_p, out.d_grad_log_p, n, stream))) return e;
+    k_ais_init_tail<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g1, out.d_log_q, out.d_log_p, d_log_q0,
+                                                                                d_log_w, d_valid, (long long)n);
+    FAB_CK_LAUNCH("k_ais_init_tail");
+    return FAB_OK;
+}
+
 int fab_hmc_step_umma_f32(const fab_flow_desc* flow, const void* d_ublob, const fab_target_desc* target,
                           fab_hmc_state st, fab_hmc_args a, fab_point cur, fab_point prop_in,
                           fab_point prop_out, float* d_log_w, const float* d_mom_noise,

@@ -401,6 +401,13 @@ int64_t fab_umma_workspace_bytes(const fab_flow_desc* flow, int64_t n);
 int fab_flow_logprob_grad_umma_f32(const fab_flow_desc* flow, const void* d_ublob, const float* d_x,
                                    float* d_log_q, float* d_grad, void* d_workspace, int64_t n,
                                    void* stream);
+/* = fab_ais_init_f32 with with_grad = 1 (d_log_q0 required): the flow sample on the tile engine, the
+ * inverse-pass log q + input-gradient on the row-tile engine, streaming target kernel, log-weight /
+ * validity tail.  d_workspace: fab_umma_workspace_bytes(flow, n). */
+int fab_ais_init_umma_f32(const fab_flow_desc* flow, const float* d_blob, const void* d_ublob,
+                          const fab_target_desc* target, const float* d_eps, fab_gamma g1, fab_point out,
+                          float* d_log_w, float* d_log_q0, uint8_t* d_valid, void* d_workspace, int64_t n,
+                          void* stream);
 /* = fab_hmc_step_f32 (same arguments and semantics); many-well target only. */
 int fab_hmc_step_umma_f32(const fab_flow_desc* flow, const void* d_ublob, const fab_target_desc* target,
                           fab_hmc_state st, fab_hmc_args args, fab_point cur, fab_point prop_in,
