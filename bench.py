@@ -447,6 +447,33 @@ def run_gpu_arm(args):
                     log_Z_last_timed_call=info["log_Z"], ess_ais_last_timed_call=info["ess_ais"])
         if multi is not None:
             line["multi_gpu_parity"] = multi
+        if world == 1:
+            # BASELINE config 3's batch (16 384 particles) on this ONE GPU: the batch at which every SM carries
+            # row tiles (the headline batch of 2 048 per GPU fills 32 of 148) -- same step, same kernels, extra leg
+            # outside the timed region of the headline
+            try:
+                B_big = 8 * B_local
+                _, _, _, ais_big = build_gpu(cfg, device, None)
+                for _ in range(2):
+                    ais_big.sample_and_log_weights(B_big)
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                for a_, b_ in ev:
+                    a_.record(); ais_big.sample_and_log_weights(B_big); b_.record()
+                torch.cuda.synchronize()
+                ms_big = sum(a_.elapsed_time(b_) for a_, b_ in ev) / len(ev)
+                k_big = ais_big.time_transitions(B_big, repeats=1)
+                tf_big = 2.0 * Ff * cfg["L"] * B_big / (k_big * 1e-3) / 1e12
+                line["full_chip_batch"] = dict(
+                    particles=B_big, ms_per_step=ms_big, value=B_big / (ms_big * 1e-3), unit=UNIT,
+                    kernel_ms=k_big, achieved_tflops=tf_big, frac=tf_big / peaks["bf16_tflops_sustained"],
+                    pipe_frac=tf_big / (n_sm * 8192 * sm_mhz * 1e6 / 1e12 / 3),
+                    note="config 3's 16 384 particles on one GPU (strong-scaling reference point of the 8-GPU line); "
+                         "frac vs the measured bf16 cuBLAS peak (three f16 products per fp32-grade product, so the "
+                         "ceiling of this arithmetic is a third of it), pipe_frac vs the tcgen05 rate of all SMs "
+                         "(8192 FLOP/cycle/SM measured) / 3")
+                del ais_big
+            except Exception as e:           # noqa: BLE001 -- an extra leg must never cost the headline line
+                line["full_chip_batch"] = dict(error=f"{type(e).__name__}: {e}")
         if world == 1 and not args.no_cpu_baseline:
             ts, cinfo, kind = time_cpu(cfg, B_local, steps=2, warmup=1)
             cv = B_local * len(ts) / float(np.sum(ts))
