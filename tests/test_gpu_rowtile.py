@@ -84,6 +84,38 @@ def test_rowtile_results_do_not_depend_on_the_batch(rowtile):
     assert torch.equal(lq_all[137:333], lq_sub) and torch.equal(g_all[137:333], g_sub)
 
 
+def test_rowtile_more_pairs_than_sm_pairs(rowtile):
+    """16 384 particles (config 3's batch on one GPU) = 128 CTA pairs on 74 SM pairs: the second wave of
+    clusters must produce the same bits as the same rows evaluated alone -- flow value + gradient and a
+    fused HMC transition."""
+    _, _, fp = make_flows(32, 3, 10, last_std=0.02)
+    g = torch.Generator().manual_seed(21)
+    n = 16384
+    x = (torch.randn(n, 32, generator=g) * 1.3).cuda()
+    lq_all, g_all = fp.cuda_log_prob(x, with_grad=True)
+    for lo, hi in ((0, 256), (9472, 9472 + 384), (n - 200, n)):          # first wave, across the wave boundary, tail
+        lq_sub, g_sub = fp.cuda_log_prob(x[lo:hi].contiguous(), with_grad=True)
+        assert torch.equal(lq_all[lo:hi], lq_sub) and torch.equal(g_all[lo:hi], g_sub), (lo, hi)
+    assert torch.isfinite(lq_all).all()
+    _, tp = make_manywell(32)
+    M = 3
+
+    def run(xs, mom, ex):
+        op = fb.HamiltonianMonteCarlo(M, 32, fp.log_prob, tp.log_prob, alpha=2.0, epsilon=0.1, L=2).cuda()
+        op.set_eval_mode(True)
+        pt = op.create_new_point(xs.clone())        # (the transition mutates the point in place)
+        pt = fb.Point(*(t.detach().contiguous() for t in (pt.x, pt.log_q, pt.log_p, pt.grad_log_q, pt.grad_log_p)))
+        op.run(pt, 2, 0.5, noise=(mom, ex))
+        return pt
+    mom = torch.randn(1, n, 32, generator=g).cuda()
+    ex = torch.empty(1, n).exponential_(1.0, generator=g).cuda()
+    big = run(x, mom, ex)
+    lo, hi = 9472 - 128, 9472 + 256
+    sub = run(x[lo:hi].contiguous(), mom[:, lo:hi].contiguous(), ex[:, lo:hi].contiguous())
+    assert torch.equal(big.x[lo:hi], sub.x) and torch.equal(big.log_q[lo:hi], sub.log_q)
+    assert torch.equal(big.grad_log_q[lo:hi], sub.grad_log_q) and torch.equal(big.log_p[lo:hi], sub.log_p)
+
+
 def test_rowtile_repack_after_parameter_update(rowtile):
     fo64, fo, fp = make_flows(32, 2, 10, last_std=0.02)
     x = torch.randn(128, 32)
