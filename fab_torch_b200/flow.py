@@ -160,6 +160,9 @@ class B200RealNVP(TrainableDistribution):
         self._ublob_key = None
         self._uws = None
         self._plist = None              # cached parameter list (see _param_key)
+        self._perm_dev = None           # device copy of the [shifts | scales] row permutation of W3
+        self._pg_layouts = {}           # fab_flow_param_grad_layout per batch size
+        self._pg_states = {}            # persistent buffers of cuda_param_grad per batch size
         self._pack_graphs = {}          # captured repack launches (see _repack)
         self._eps_override = None       # test hook: next sample uses this base noise
         # filled lazily: needs the .so
@@ -189,6 +192,7 @@ class B200RealNVP(TrainableDistribution):
     def _apply(self, fn, *args, **kwargs):
         self._plist = None
         self._pack_graphs = {}          # parameter storage may move: the captured pointers go stale
+        self._pg_states = {}
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
@@ -265,18 +269,6 @@ class B200RealNVP(TrainableDistribution):
             U_inv = torch.linalg.solve_triangular(U.double(), eye64, upper=True).float()
             W_inv = U_inv @ L_inv @ P.transpose(1, 2)
         return W, W_inv, log_S.sum(dim=1)
-
-    def _mixing_W(self):
-        """W [K,d,d] and sum(log_S) [K] only (differentiable w.r.t. L, U, log_S)."""
-        mixes = [self._nf_model.flows[2 * k + 1] for k in range(self.n_flow_layers)]
-        P = torch.stack([m.P for m in mixes])
-        eye = mixes[0].eye
-        L = torch.tril(torch.stack([m.L for m in mixes]), diagonal=-1) + eye
-        log_S = torch.stack([m.log_S for m in mixes])
-        sign_S = torch.stack([m.sign_S for m in mixes])
-        U = torch.triu(torch.stack([m.U for m in mixes]), diagonal=1) + \
-            torch.diag_embed(sign_S * torch.exp(log_S))
-        return P @ L @ U, log_S.sum(dim=1)
 
     def _pack(self) -> torch.Tensor:
         d = self.desc()
@@ -471,9 +463,11 @@ class B200RealNVP(TrainableDistribution):
     # ---- parameter gradient (csrc/param_grad.cuh) ------------------------------------------------
     def _pg_layout(self, n: int):
         import ctypes as C
-        offs = (C.c_int64 * 20)()
-        _lib.check(_lib.lib().fab_flow_param_grad_layout(self.desc(), n, offs), "fab_flow_param_grad_layout")
-        return [int(v) for v in offs]
+        if n not in self._pg_layouts:
+            offs = (C.c_int64 * 20)()
+            _lib.check(_lib.lib().fab_flow_param_grad_layout(self.desc(), n, offs), "fab_flow_param_grad_layout")
+            self._pg_layouts[n] = [int(v) for v in offs]
+        return self._pg_layouts[n]
 
     def cuda_log_prob_tape(self, x: torch.Tensor, with_grad: bool):
         """log q, (optionally) d log q / dx and the activation tape of the parameter gradient."""
@@ -489,56 +483,110 @@ class B200RealNVP(TrainableDistribution):
         _lib.check(rc, "fab_flow_logprob_tape_f32")
         return log_q, grad, tape
 
-    def cuda_param_grad(self, tape: torch.Tensor, g: torch.Tensor):
-        """Gradients of sum_i g_i log q(x_i) for every parameter, in `self.parameters()` order."""
-        n = g.shape[0]
+    def _pg_state(self, n: int, dev):
+        """Per batch size: the kernels' output / workspace buffers and the flat gradient buffer (in
+        `self.parameters()` order) the chain rule writes.  The buffers are persistent so that the chain
+        rule -- ~40 small torch launches -- can be replayed as one CUDA graph (`_repack`)."""
+        st = self._pg_states.get(n)
+        if st is not None and st["out"].device == dev:
+            return st
         offs = self._pg_layout(n)
-        total, LS, oa, ob, oc, od, tail_off, ws = offs[10], offs[11], offs[12], offs[13], offs[14], offs[15], offs[16], offs[17]
-        dev = tape.device
-        out = torch.empty(total, dtype=torch.float32, device=dev)
-        wsb = torch.empty(max(ws, 1), dtype=torch.float32, device=dev)
-        g = _lib.f32(g).contiguous()
-        rc = _lib.lib().fab_flow_param_grad_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(tape), _lib.ptr(g), n,
-                                                _lib.ptr(out), _lib.ptr(wsb), _lib.stream_ptr(dev))
-        _lib.check(rc, "fab_flow_param_grad_f32")
+        ps = list(self.parameters())
+        sizes = [p.numel() for p in ps]
+        starts = [0]
+        for sz in sizes:
+            starts.append(starts[-1] + sz)
+        st = dict(offs=offs, out=torch.empty(offs[10], dtype=torch.float32, device=dev),
+                  ws=torch.empty(max(offs[17], 1), dtype=torch.float32, device=dev),
+                  res=torch.zeros(starts[-1], dtype=torch.float32, device=dev),
+                  slices=[(starts[i], starts[i + 1], tuple(p.shape)) for i, p in enumerate(ps)],
+                  start={id(p): starts[i] for i, p in enumerate(ps)})
+        if len(self._pg_states) >= 8:             # training uses one or two batch sizes; bound the rest
+            old = next(iter(self._pg_states))
+            del self._pg_states[old]
+            self._pack_graphs.pop(f"pg{old}", None)
+        self._pg_states[n] = st
+        self._pack_graphs.pop(f"pg{n}", None)
+        return st
+
+    def _pg_dst(self, st, params):
+        """View of the flat gradient buffer covering the same parameter of every layer, [K, *shape]."""
+        K = len(params)
+        o = [st["start"][id(p)] for p in params]
+        shape = tuple(params[0].shape)
+        step = o[1] - o[0] if K > 1 else params[0].numel()
+        if any(o[k] != o[0] + k * step for k in range(K)) or any(tuple(p.shape) != shape for p in params):
+            raise RuntimeError("flow layers do not share one parameter layout")
+        strides, acc = [], 1
+        for sz in reversed(shape):
+            strides.append(acc)
+            acc *= sz
+        return torch.as_strided(st["res"], (K,) + shape, (step,) + tuple(reversed(strides)), o[0])
+
+    def _pg_chain(self, st):
+        """Chain rule in parameter space, batched over the layers: kernel output (`param_grad.cuh`:
+        Ga, Gb, Gc, Gd, base tail) -> gradients of the module's parameters, written into st['res'].
+        W = P Lf Uf with Lf = tril(L, -1) + I, Uf = triu(U, 1) + diag(sign_S exp(log_S)):
+          dL = tril(P^T dW Uf^T, -1),  dU = triu(Lf^T P^T dW, 1),
+          dlog_S = diag(Lf^T P^T dW) sign_S exp(log_S) + sum_i g_i    (sum(log_S) enters log q directly)."""
+        offs, out, res = st["offs"], st["out"], st["res"]
+        LS, oa, ob, oc, od, tail_off = offs[11], offs[12], offs[13], offs[14], offs[15], offs[16]
         K, d, W = self.n_flow_layers, self.dim, self.width
         dsc = self.desc()
         d1, p2 = dsc.d1, 2 * dsc.d2
         q0 = self._nf_model.q0
-        grads = {id(q0.loc): out[tail_off:tail_off + d].view(1, d),
-                 id(q0.log_scale): out[tail_off + d:tail_off + 2 * d].view(1, d)}
-        if K:
-            lay = out[:K * LS].view(K, LS)
-            Ga = lay[:, oa:oa + (d + 1) * W].view(K, d + 1, W)
-            Gb = lay[:, ob:ob + d * d].view(K, d, d)
-            Gc = lay[:, oc:oc + W * (W + 1)].view(K, W, W + 1)
-            Gd = lay[:, od:od + p2 * (W + 1)].view(K, p2, W + 1)
-            blocks = [self._nf_model.flows[2 * k] for k in range(K)]
-            mixes = [self._nf_model.flows[2 * k + 1] for k in range(K)]
-            with torch.enable_grad():
-                Wm, logs = self._mixing_W()
-            W1 = torch.stack([b.linears[0].weight.detach() for b in blocks])          # [K, W, d1]
-            dM1 = Ga[:, :d, :]                                                          # [K, d, W]
-            dW1 = dM1.transpose(1, 2) @ Wm.detach()[:, :, :d1]                          # [K, W, d1]
-            dWm = Gb.clone()
-            dWm[:, :, :d1] += dM1 @ W1
-            perm = torch.cat([torch.arange(0, p2, 2), torch.arange(1, p2, 2)]).to(dev)
-            dW3 = torch.empty(K, p2, W, dtype=torch.float32, device=dev)
-            db3 = torch.empty(K, p2, dtype=torch.float32, device=dev)
-            dW3[:, perm, :] = Gd[:, :, :W]
-            db3[:, perm] = Gd[:, :, W]
-            mix_params = [p for m in mixes for p in (m.L, m.log_S, m.U)]
-            sum_g = out[tail_off + 2 * d]
-            with torch.enable_grad():
-                mg = torch.autograd.grad([Wm, logs], mix_params, grad_outputs=[dWm, sum_g.expand(K)])
-            for k in range(K):
-                l1, l2, l3 = blocks[k].linears
-                grads[id(l1.weight)] = dW1[k]; grads[id(l1.bias)] = Ga[k, d, :]
-                grads[id(l2.weight)] = Gc[k, :, :W]; grads[id(l2.bias)] = Gc[k, :, W]
-                grads[id(l3.weight)] = dW3[k]; grads[id(l3.bias)] = db3[k]
-            for p, gr in zip(mix_params, mg):
-                grads[id(p)] = gr
-        return [grads[id(p)] for p in self.parameters()]
+        s0 = st["start"][id(q0.loc)]
+        res[s0:s0 + d].copy_(out[tail_off:tail_off + d])
+        s0 = st["start"][id(q0.log_scale)]
+        res[s0:s0 + d].copy_(out[tail_off + d:tail_off + 2 * d])
+        if not K:
+            return
+        dev = out.device
+        lay = out[:K * LS].view(K, LS)
+        Ga = lay[:, oa:oa + (d + 1) * W].view(K, d + 1, W)
+        Gb = lay[:, ob:ob + d * d].view(K, d, d)
+        Gc = lay[:, oc:oc + W * (W + 1)].view(K, W, W + 1)
+        Gd = lay[:, od:od + p2 * (W + 1)].view(K, p2, W + 1)
+        blocks = [self._nf_model.flows[2 * k] for k in range(K)]
+        mixes = [self._nf_model.flows[2 * k + 1] for k in range(K)]
+        P = torch.stack([m.P for m in mixes])
+        Lf = torch.tril(torch.stack([m.L.detach() for m in mixes]), diagonal=-1) + mixes[0].eye
+        sdiag = torch.stack([m.sign_S for m in mixes]) * torch.exp(torch.stack([m.log_S.detach() for m in mixes]))
+        Uf = torch.triu(torch.stack([m.U.detach() for m in mixes]), diagonal=1) + torch.diag_embed(sdiag)
+        Wm = P @ Lf @ Uf
+        W1 = torch.stack([b.linears[0].weight.detach() for b in blocks])              # [K, W, d1]
+        dM1 = Ga[:, :d, :]                                                              # [K, d, W]
+        self._pg_dst(st, [b.linears[0].weight for b in blocks]).copy_(dM1.transpose(1, 2) @ Wm[:, :, :d1])
+        self._pg_dst(st, [b.linears[0].bias for b in blocks]).copy_(Ga[:, d, :])
+        self._pg_dst(st, [b.linears[1].weight for b in blocks]).copy_(Gc[:, :, :W])
+        self._pg_dst(st, [b.linears[1].bias for b in blocks]).copy_(Gc[:, :, W])
+        if self._perm_dev is None or self._perm_dev.device != dev:
+            self._perm_dev = torch.cat([torch.arange(0, p2, 2, device=dev), torch.arange(1, p2, 2, device=dev)])
+        perm = self._perm_dev                     # kernel rows: shifts then scales; torch rows interleave them
+        self._pg_dst(st, [b.linears[2].weight for b in blocks])[:, perm, :] = Gd[:, :, :W]
+        self._pg_dst(st, [b.linears[2].bias for b in blocks])[:, perm] = Gd[:, :, W]
+        dWm = Gb.clone()
+        dWm[:, :, :d1] += dM1 @ W1
+        A = P.transpose(1, 2) @ dWm
+        dUf = Lf.transpose(1, 2) @ A
+        self._pg_dst(st, [m.L for m in mixes]).copy_(torch.tril(A @ Uf.transpose(1, 2), diagonal=-1))
+        self._pg_dst(st, [m.U for m in mixes]).copy_(torch.triu(dUf, diagonal=1))
+        self._pg_dst(st, [m.log_S for m in mixes]).copy_(
+            torch.diagonal(dUf, dim1=1, dim2=2) * sdiag + out[tail_off + 2 * d])
+
+    def cuda_param_grad(self, tape: torch.Tensor, g: torch.Tensor):
+        """Gradients of sum_i g_i log q(x_i) for every parameter, in `self.parameters()` order."""
+        n = g.shape[0]
+        dev = tape.device
+        st = self._pg_state(n, dev)
+        g = _lib.f32(g).contiguous()
+        rc = _lib.lib().fab_flow_param_grad_f32(self.desc(), _lib.ptr(self.blob()), _lib.ptr(tape), _lib.ptr(g), n,
+                                                _lib.ptr(st["out"]), _lib.ptr(st["ws"]), _lib.stream_ptr(dev))
+        _lib.check(rc, "fab_flow_param_grad_f32")
+        with torch.no_grad():
+            self._repack(f"pg{n}", lambda: self._pg_chain(st))
+            flat = st["res"].clone()              # the persistent buffer is overwritten by the next call
+        return [flat[a:b].view(shape) for a, b, shape in st["slices"]]
 
     # ---- the same maths in torch ops (GPU), differentiable w.r.t. parameters -----------------
     def _coupling_params(self, k, v1):

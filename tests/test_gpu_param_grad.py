@@ -77,3 +77,32 @@ def test_param_grad_with_input_grad_and_repeat():
     assert _tensor_err(outs[0][-1], x64.grad) < 5e-5
     for p1, p2 in zip(fp.parameters(), fo64.parameters()):
         assert _tensor_err(p1.grad, p2.grad) < 1e-4
+
+
+def test_param_grad_follows_parameter_updates_through_the_captured_chain_rule():
+    """The parameter-space chain rule runs eagerly on the first call, is captured into a CUDA graph on
+    the second and replayed afterwards (flow.py: cuda_param_grad / _repack).  With an optimiser step
+    between the calls every one of them must give the gradient at the CURRENT parameters, and the
+    gradients handed out earlier must not change when the persistent buffer is overwritten."""
+    fo64, fo, fp = make_flows(6, 3, 8)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(200, 6, generator=g)
+    w = torch.softmax(torch.randn(200, generator=g), 0)
+    kept = []
+    for it in range(5):
+        fp.zero_grad()
+        fo64.zero_grad()
+        (-(w.cuda() * fp.log_prob(x.cuda())).mean()).backward()
+        (-(w.double() * fo64.log_prob(x.double())).mean()).backward()
+        for (n1, p1), (n2, p2) in zip(fp.named_parameters(), fo64.named_parameters()):
+            assert _tensor_err(p1.grad, p2.grad) < 1e-4, f"call {it}: {n1}"
+        kept.append(([p.grad for p in fp.parameters()], [p.grad.clone() for p in fp.parameters()]))
+        with torch.no_grad():
+            for p1, p2 in zip(fp.parameters(), fo64.parameters()):
+                step = 0.05 * torch.randn(p2.shape, generator=g, dtype=torch.float64)
+                p2.add_(step)
+                p1.add_(step.float().cuda())
+    assert f"pg{len(x)}" in fp._pack_graphs and fp._pack_graphs[f"pg{len(x)}"]["graph"] is not None
+    for held, copies in kept:
+        for a, b in zip(held, copies):
+            assert torch.equal(a, b)
