@@ -29,7 +29,8 @@ class FlowDesc(C.Structure):
                 ("o_mw1", C.c_int64), ("o_w2", C.c_int64), ("o_w3", C.c_int64),
                 ("o_w3t", C.c_int64), ("o_w2t", C.c_int64), ("o_w1mt", C.c_int64),
                 ("o_w1", C.c_int64), ("o_mix_inv", C.c_int64),
-                ("o_b1", C.c_int64), ("o_b2", C.c_int64), ("o_b3", C.c_int64), ("o_logs", C.c_int64)]
+                ("o_b1", C.c_int64), ("o_b2", C.c_int64), ("o_b3", C.c_int64), ("o_logs", C.c_int64),
+                ("o_b1s", C.c_int64), ("o_tmix", C.c_int64)]
 
 
 class TargetDesc(C.Structure):

@@ -129,6 +129,8 @@ int64_t fab_flow_desc_init(fab_flow_desc* d, int32_t dim, int32_t width, int32_t
     d->o_b2 = l;      l += W8;
     d->o_b3 = l;      l += P8;
     d->o_logs = l;    l += 4;
+    d->o_b1s = l;     l += W8;
+    d->o_tmix = l;    l += D8;
     d->layer_stride = l;
     d->total_floats = o + (int64_t)n_layers * l + 512;     // tail pad: L1 prefetches may run past the end
     return d->total_floats;
@@ -290,13 +292,13 @@ struct PgLayout {            // dense gradient buffer: [K layers][Ga | Gb | Gc |
 PgLayout pg_layout(const fab_flow_desc& f, int64_t n) {
     PgLayout P{};
     const int64_t d = f.dim, W = f.width, p2 = 2 * f.d2;
-    P.oa = 0; P.ob = P.oa + (d + 1) * W; P.oc = P.ob + d * d; P.od = P.oc + W * (W + 1);
+    P.oa = 0; P.ob = P.oa + (d + 1) * W; P.oc = P.ob + (d + 1) * d; P.od = P.oc + W * (W + 1);
     P.layer_floats = P.od + p2 * (W + 1);
     P.tail_off = P.layer_floats * f.n_layers;
     P.total = P.tail_off + 2 * d + 1;
     P.rows_per_split = 256;
     P.splits = (int)std::max<int64_t>(1, (n + P.rows_per_split - 1) / P.rows_per_split);
-    const int64_t mx = std::max<int64_t>({(d + 1) * W, d * d, W * (W + 1), p2 * (W + 1)});
+    const int64_t mx = std::max<int64_t>({(d + 1) * W, (d + 1) * d, W * (W + 1), p2 * (W + 1)});
     P.ws_floats = mx * P.splits * std::max(1, f.n_layers);
     return P;
 }
@@ -357,7 +359,7 @@ int fab_flow_param_grad_f32(const fab_flow_desc* flow, const float* d_blob, cons
     };
     if (K > 0) {
         if (int e = gemm(tape.o_z, d + 1, tape.o_gh1, W, P.oa)) return e;
-        if (int e = gemm(tape.o_z, d, tape.o_gv, d, P.ob)) return e;
+        if (int e = gemm(tape.o_z, d + 1, tape.o_gv, d, P.ob)) return e;
         if (int e = gemm(tape.o_gh2, W, tape.o_h1, W + 1, P.oc)) return e;
         if (int e = gemm(tape.o_gpar, p2, tape.o_h2, W + 1, P.od)) return e;
     }

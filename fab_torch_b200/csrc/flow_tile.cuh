@@ -415,7 +415,7 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
         {
             float* h1 = b.h1;
             mma_gemm_wide<TP>(z, L.D1K / 16, reinterpret_cast<const float4*>(lay + f.o_w1), L.NTH,
-                              lay + f.o_b1 + L.D8, [&](int nt, const float (&c)[4]) {
+                              lay + f.o_b1s, [&](int nt, const float (&c)[4]) {
                                   hidden_fwd<TP, false>(h1, nullptr, nt, g, t, c);
                               });
         }
@@ -434,7 +434,7 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
             }
         }
         __syncthreads();
-        // u' = [v1,y2] @ Wmix^-1
+        // u' = [v1,y2] @ Wmix^-1 + t   (t: the folded ActNorm shift, zero without ActNorm)
         const int KS2 = mma_gemm_ksplit<TP>(z, L.D16 / 16, reinterpret_cast<const float4*>(lay + f.o_mix_inv),
                                             L.D8 / 8, b.red);
         if (k + 1 < L.K)
@@ -442,7 +442,7 @@ __device__ void flow_sample(const TileLayout& L, const fab_flow_desc& f,
         __syncthreads();
         for (int e = threadIdx.x; e < L.d * TP; e += FAB_NT) {
             const int j = e / TP, p = e - j * TP;
-            z[(size_t)j * S + p] = red_sum<TP>(b.red, KS2, L.D8, p, j);
+            z[(size_t)j * S + p] = red_sum<TP>(b.red, KS2, L.D8, p, j) + __ldg(lay + f.o_tmix + j);
         }
         __syncthreads();
     }

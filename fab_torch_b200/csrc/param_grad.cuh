@@ -11,7 +11,7 @@
 //         C[m][n] = sum_i g_i A[i][m] B[i][n],        A, B = column ranges of the tape rows,
 //      four per layer (the ones columns of the tape turn bias gradients into extra rows/columns):
 //         Ga = [z_in | 1]^T gh1    (d+1) x W     rows 0..d-1: dM1 = d/d(Wmix[:, :d1] W1^T), row d: db1
-//         Gb =  z_in^T      gv      d x d        direct part of dWmix
+//         Gb = [z_in | 1]^T gv     (d+1) x d     direct part of dWmix; row d: gradient of the bias of v
 //         Gc =  gh2^T      [h1 | 1]  W x (W+1)   dW2 (torch layout [out][in]) | db2
 //         Gd =  gparam^T   [h2 | 1]  2d2 x (W+1) dW3 (rows: shifts, then scales) | db3
 //      fp32 FMA tiles (64 x 64 per CTA, 4 x 4 per thread), the batch split over blockIdx.y into

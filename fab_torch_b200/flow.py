@@ -85,8 +85,19 @@ class _InvertibleAffine(nn.Module):
         self.register_buffer("eye", torch.diag(torch.ones(dim)))
 
 
+class _ActNorm(nn.Module):
+    """normflows' ActNorm(dim): z * exp(s) + t, parameters of shape [1, d]; `data_dep_init_done`
+    flips to 1 once s, t have been set from the statistics of the first batch."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.s = nn.Parameter(torch.zeros(1, dim))
+        self.t = nn.Parameter(torch.zeros(1, dim))
+        self.register_buffer("data_dep_init_done", torch.tensor(0.0))
+
+
 class _NFModel(nn.Module):
-    def __init__(self, dim, n_layers, width):
+    def __init__(self, dim, n_layers, width, act_norm=False):
         super().__init__()
         self.q0 = _DiagGaussian(dim)
         d1 = int((dim / 2) + 0.5)
@@ -94,6 +105,8 @@ class _NFModel(nn.Module):
         for _ in range(n_layers):
             flows.append(_CouplingBlock(_MLP([d1, width, width, 2 * (dim - d1)])))
             flows.append(_InvertibleAffine(dim))
+            if act_norm:
+                flows.append(_ActNorm(dim))
         self.flows = nn.ModuleList(flows)
 
 
@@ -140,19 +153,23 @@ def _pad_last(v: torch.Tensor, n: int) -> torch.Tensor:
 
 class B200RealNVP(TrainableDistribution):
     """Drop-in for `make_wrapped_normflow_realnvp(dim, n_flow_layers, layer_nodes_per_dim,
-    act_norm=False)` (make_normflow_model.py:82-96)."""
+    act_norm)` (make_normflow_model.py:82-96).
+
+    `act_norm=True` appends an ActNorm layer (z * exp(s) + t) to every block (make_normflow_model.py:
+    28-29) and, like the reference factory (:94-95), draws 500 samples once to set s, t from the
+    batch statistics.  The kernels never see the layer: the host folds it into the block's linear
+    part (Wmix := diag(exp(-s)) W, bias c = -t @ Wmix, log|det| = sum(log_S) - sum(s); include/
+    fab_b200.h) when it packs the weights.  With ActNorm the warp-level engine evaluates the flow
+    (the row-tile engine's issue program has no bias row for the v columns)."""
 
     def __init__(self, dim: int, n_flow_layers: int = 5, layer_nodes_per_dim: int = 10,
                  act_norm: bool = False):
         super().__init__()
-        if act_norm:
-            raise NotImplementedError(
-                "act_norm=True is not supported by the B200 path (every shipped reference config "
-                "sets flow.act_norm: false)")
         self.dim = dim
         self.n_flow_layers = n_flow_layers
         self.width = dim * layer_nodes_per_dim
-        self._nf_model = _NFModel(dim, n_flow_layers, self.width)
+        self.act_norm = bool(act_norm) and n_flow_layers > 0
+        self._nf_model = _NFModel(dim, n_flow_layers, self.width, self.act_norm)
         self._desc = _lib.FlowDesc()
         self._blob = None
         self._blob_key = None
@@ -167,6 +184,45 @@ class B200RealNVP(TrainableDistribution):
         self._eps_override = None       # test hook: next sample uses this base noise
         # filled lazily: needs the .so
         self._desc_ready = False
+        if self.act_norm:
+            self._init_act_norm(500)
+
+    # ---- layer access ------------------------------------------------------------------
+    def _blocks(self):
+        st = 3 if self.act_norm else 2
+        return [self._nf_model.flows[st * k] for k in range(self.n_flow_layers)]
+
+    def _mixes(self):
+        st = 3 if self.act_norm else 2
+        return [self._nf_model.flows[st * k + 1] for k in range(self.n_flow_layers)]
+
+    def _acts(self):
+        return [self._nf_model.flows[3 * k + 2] for k in range(self.n_flow_layers)] if self.act_norm else []
+
+    @torch.no_grad()
+    def _init_act_norm(self, n: int):
+        """Data-dependent initialisation of the ActNorm layers (normflows ActNorm.forward on its first
+        call, triggered by `sample((500,))` in make_normflow_model.py:94-95): walking the layers in the
+        sampling direction, s = -log(std + 1e-6), t = -mean * exp(s) of the layer's input batch.
+        One-time parameter initialisation in torch ops on the parameters' device (consumes
+        randn(n, d) from the global generator, like the reference's call)."""
+        q0 = self._nf_model.q0
+        d1 = int((self.dim / 2) + 0.5)
+        z = q0.loc + torch.exp(q0.log_scale) * torch.randn((n, self.dim), dtype=q0.loc.dtype, device=q0.loc.device)
+        for blk, mix, act in zip(self._blocks(), self._mixes(), self._acts()):
+            l1, l2, l3 = blk.linears
+            z1, z2 = z[:, :d1], z[:, d1:]
+            par = l3(torch.relu(l2(torch.relu(l1(z1)))))
+            z = torch.cat([z1, z2 * torch.exp(par[:, 1::2]) + par[:, 0::2]], dim=1)
+            Lf = torch.tril(mix.L, diagonal=-1) + mix.eye
+            Uf = torch.triu(mix.U, diagonal=1) + torch.diag(mix.sign_S * torch.exp(mix.log_S))
+            W_inv = torch.inverse(Uf.double()).to(z.dtype) @ torch.inverse(Lf.double()).to(z.dtype) @ mix.P.t()
+            z = z @ W_inv
+            if not act.data_dep_init_done > 0.0:
+                act.s.copy_(-torch.log(z.std(dim=0, keepdim=True) + 1e-6))
+                act.t.copy_(-z.mean(dim=0, keepdim=True) * torch.exp(act.s))
+                act.data_dep_init_done.fill_(1.0)
+            z = z * torch.exp(act.s) + act.t
 
     # ---- descriptor / blob -------------------------------------------------------------
     def desc(self) -> "_lib.FlowDesc":
@@ -233,10 +289,31 @@ class B200RealNVP(TrainableDistribution):
             self._blob_key = key
         return self._blob
 
+    def _act_st(self):
+        """(s, t) of the ActNorm layers, [K, d] each; None without ActNorm."""
+        if not self.act_norm:
+            return None, None
+        acts = self._acts()
+        return torch.stack([a.s.reshape(-1) for a in acts]), torch.stack([a.t.reshape(-1) for a in acts])
+
+    def _fold_act(self, W, W_inv, logs):
+        """ActNorm folded into the block's linear part: in the log_prob direction the block starts with
+        ((z - t) exp(-s)) @ W = z @ W' + c, W' = diag(exp(-s)) W, c = -t @ W'; when sampling it ends with
+        (z @ W^-1) exp(s) + t = z @ W'^-1 + t.  Returns (W', W'^-1, log|det|, c, t); c = t = None
+        without ActNorm."""
+        s_, t_ = self._act_st()
+        if s_ is None:
+            return W, W_inv, logs, None, None
+        s_, t_ = s_.to(W.dtype), t_.to(W.dtype)
+        We = torch.exp(-s_)[:, :, None] * W
+        We_inv = W_inv * torch.exp(s_)[:, None, :] if W_inv is not None else None
+        c = -(t_[:, None, :] @ We)[:, 0, :]
+        return We, We_inv, logs - s_.sum(dim=1), c, t_
+
     def _mixing(self, dtype=torch.float32):
-        """Stacked W, W^-1 [K,d,d] and sum(log_S) [K], assembled exactly like normflows'
-        InvertibleAffine._assemble_W (inverse of L and U in float64, then cast)."""
-        mixes = [self._nf_model.flows[2 * k + 1] for k in range(self.n_flow_layers)]
+        """Effective W [K,d,d], W^-1 and log|det| [K] of every block's linear part plus the biases
+        (c, t) of `_fold_act` (differentiable)."""
+        mixes = self._mixes()
         P = torch.stack([m.P for m in mixes])
         eye = mixes[0].eye
         L = torch.tril(torch.stack([m.L for m in mixes]), diagonal=-1) + eye
@@ -248,12 +325,12 @@ class B200RealNVP(TrainableDistribution):
         L_inv = torch.inverse(L.double()).to(dtype)
         U_inv = torch.inverse(U.double()).to(dtype)
         W_inv = U_inv @ L_inv @ P.transpose(1, 2)
-        return W, W_inv, log_S.sum(dim=1)
+        return self._fold_act(W, W_inv, log_S.sum(dim=1))
 
     def _mixing_pack(self, need_inverse: bool = True):
         """`_mixing` for the weight packers: no autograd, and the float64 inverses of the triangular
         factors by triangular solves (no pivoting, no host-side info check: capturable in a CUDA graph)."""
-        mixes = [self._nf_model.flows[2 * k + 1] for k in range(self.n_flow_layers)]
+        mixes = self._mixes()
         P = torch.stack([m.P for m in mixes])
         eye = mixes[0].eye
         L = torch.tril(torch.stack([m.L for m in mixes]), diagonal=-1) + eye
@@ -268,7 +345,7 @@ class B200RealNVP(TrainableDistribution):
             L_inv = torch.linalg.solve_triangular(L.double(), eye64, upper=False).float()
             U_inv = torch.linalg.solve_triangular(U.double(), eye64, upper=True).float()
             W_inv = U_inv @ L_inv @ P.transpose(1, 2)
-        return W, W_inv, log_S.sum(dim=1)
+        return self._fold_act(W, W_inv, log_S.sum(dim=1))
 
     def _pack(self) -> torch.Tensor:
         d = self.desc()
@@ -284,7 +361,7 @@ class B200RealNVP(TrainableDistribution):
         tail = base.new_zeros(512)
         if K == 0:
             return torch.cat([base, tail]).contiguous()
-        blocks = [self._nf_model.flows[2 * k] for k in range(K)]
+        blocks = self._blocks()
         W1 = torch.stack([b.linears[0].weight for b in blocks])     # [K, W, d1]
         b1 = torch.stack([b.linears[0].bias for b in blocks])
         W2 = torch.stack([b.linears[1].weight for b in blocks])     # [K, W, W]
@@ -294,7 +371,7 @@ class B200RealNVP(TrainableDistribution):
         perm = torch.cat([torch.arange(0, 2 * d.d2, 2, device=dev), torch.arange(1, 2 * d.d2, 2, device=dev)])
         W3 = W3[:, perm, :]
         b3 = b3[:, perm]
-        Wm, Wm_inv, logs = self._mixing_pack()
+        Wm, Wm_inv, logs, cmix, tmix = self._mixing_pack()
         t = lambda M: M.transpose(1, 2)
         dd, d1, W = d.dim, d.d1, d.width
         z = lambda r, c: W1.new_zeros(K, r, c)
@@ -305,8 +382,11 @@ class B200RealNVP(TrainableDistribution):
         w1mt = z(W16 + dd, dd)                         # o_w1mt: [gh1 | gv] -> g_u
         w1mt[:, :W, :] = (W1.double() @ t(Wm[:, :, :d1]).double()).float()
         w1mt[:, W16:W16 + dd, :] = t(Wm)
-        b1e = z(1, D8 + W8)[:, 0]                      # o_b1: [0 | b1]
+        b1e = z(1, D8 + W8)[:, 0]                      # o_b1: [c | b1 + c[:d1] @ W1^T]   (c = 0 without ActNorm)
         b1e[:, D8:D8 + W] = b1
+        if cmix is not None:
+            b1e[:, :dd] = cmix
+            b1e[:, D8:D8 + W] = (b1.double() + (cmix[:, None, :d1].double() @ t(W1).double())[:, 0, :]).float()
         parts = [
             _pack_frag(mw1, D16, D8 + W8),
             _pack_frag(t(W2), W16, W8),                # o_w2      M[k][n] = W2[n][k]
@@ -320,6 +400,8 @@ class B200RealNVP(TrainableDistribution):
             _pad_last(b2, W8),
             _pad_last(b3, P8),
             _pad_last(logs[:, None], 4),
+            _pad_last(b1, W8),                         # o_b1s
+            _pad_last(tmix, D8) if tmix is not None else z(1, D8)[:, 0],   # o_tmix
         ]
         layers = torch.cat(parts, dim=1)
         assert layers.shape[1] == d.layer_stride, (layers.shape, d.layer_stride)
@@ -329,7 +411,7 @@ class B200RealNVP(TrainableDistribution):
 
     # ---- row-tile engine (tcgen05): weight images and engine choice ------------------------------
     def rowtile_supported(self) -> bool:
-        return bool(_lib.lib().fab_umma_supported(self.desc()))
+        return not self.act_norm and bool(_lib.lib().fab_umma_supported(self.desc()))
 
     def use_rowtile(self, n: int) -> bool:
         mode = _lib.engine_choice()
@@ -338,7 +420,7 @@ class B200RealNVP(TrainableDistribution):
         if not self.rowtile_supported():
             if mode == "rowtile":
                 raise RuntimeError("FAB_ENGINE=rowtile: this flow shape is not covered by the row-tile "
-                                   "engine (needs dim 32, width 64..320 in steps of 64, <= 10 layers)")
+                                   "engine (needs dim 32, width 64..320 in steps of 64, <= 10 layers, no ActNorm)")
             return False
         return mode == "rowtile" or n >= _lib.rowtile_min_n()
 
@@ -374,7 +456,7 @@ class B200RealNVP(TrainableDistribution):
         _lib.check(_lib.lib().fab_umma_plain_layout(d, offs), "fab_umma_plain_layout")
         total, off_layers, per_layer, logs_off = (int(offs[i]) for i in range(4))
         K, dd, d1, W = self.n_flow_layers, d.dim, d.d1, d.width
-        blocks = [self._nf_model.flows[2 * k] for k in range(K)]
+        blocks = self._blocks()
         W1 = torch.stack([b.linears[0].weight for b in blocks])     # [K, W, d1]
         b1 = torch.stack([b.linears[0].bias for b in blocks])
         W2 = torch.stack([b.linears[1].weight for b in blocks])     # [K, W, W]
@@ -384,7 +466,7 @@ class B200RealNVP(TrainableDistribution):
         dev = W1.device
         perm = torch.cat([torch.arange(0, 2 * d.d2, 2, device=dev), torch.arange(1, 2 * d.d2, 2, device=dev)])
         W3, b3 = W3[:, perm, :], b3[:, perm]
-        Wm, _, logs = self._mixing_pack(need_inverse=False)
+        Wm, _, logs, _, _ = self._mixing_pack(need_inverse=False)
         t = lambda M: M.transpose(1, 2)
         mw1 = torch.cat([Wm, (Wm[:, :, :d1].double() @ t(W1).double()).float()], dim=2)   # [K, d, d+W]
         b1e = torch.cat([b1.new_zeros(K, dd), b1], dim=1)
@@ -544,20 +626,39 @@ class B200RealNVP(TrainableDistribution):
         dev = out.device
         lay = out[:K * LS].view(K, LS)
         Ga = lay[:, oa:oa + (d + 1) * W].view(K, d + 1, W)
-        Gb = lay[:, ob:ob + d * d].view(K, d, d)
+        Gb = lay[:, ob:ob + (d + 1) * d].view(K, d + 1, d)
         Gc = lay[:, oc:oc + W * (W + 1)].view(K, W, W + 1)
         Gd = lay[:, od:od + p2 * (W + 1)].view(K, p2, W + 1)
-        blocks = [self._nf_model.flows[2 * k] for k in range(K)]
-        mixes = [self._nf_model.flows[2 * k + 1] for k in range(K)]
+        blocks, mixes, acts = self._blocks(), self._mixes(), self._acts()
+        sum_g = out[tail_off + 2 * d]
         P = torch.stack([m.P for m in mixes])
         Lf = torch.tril(torch.stack([m.L.detach() for m in mixes]), diagonal=-1) + mixes[0].eye
         sdiag = torch.stack([m.sign_S for m in mixes]) * torch.exp(torch.stack([m.log_S.detach() for m in mixes]))
         Uf = torch.triu(torch.stack([m.U.detach() for m in mixes]), diagonal=1) + torch.diag_embed(sdiag)
-        Wm = P @ Lf @ Uf
+        Wm = P @ Lf @ Uf                                                                # the kernels' Wmix ...
+        if acts:                                                                        # ... = diag(exp(-s)) W with ActNorm
+            s_ = torch.stack([a.s.detach().reshape(-1) for a in acts])
+            t_ = torch.stack([a.t.detach().reshape(-1) for a in acts])
+            es = torch.exp(-s_)
+            Wm = es[:, :, None] * Wm
         W1 = torch.stack([b.linears[0].weight.detach() for b in blocks])              # [K, W, d1]
         dM1 = Ga[:, :d, :]                                                              # [K, d, W]
-        self._pg_dst(st, [b.linears[0].weight for b in blocks]).copy_(dM1.transpose(1, 2) @ Wm[:, :, :d1])
-        self._pg_dst(st, [b.linears[0].bias for b in blocks]).copy_(Ga[:, d, :])
+        db1 = Ga[:, d, :]                                                               # [K, W]
+        dW1 = dM1.transpose(1, 2) @ Wm[:, :, :d1]
+        dWm = Gb[:, :d, :].clone()
+        dWm[:, :, :d1] += dM1 @ W1
+        if acts:
+            # v = z @ Wmix + c and h1pre = z @ M1 + (b1 + c[:d1] @ W1^T) with c = -t @ Wmix
+            c = -(t_[:, None, :] @ Wm)[:, 0, :]
+            dW1 = dW1 + db1[:, :, None] * c[:, None, :d1]
+            dc = Gb[:, d, :].clone()
+            dc[:, :d1] += (db1[:, None, :] @ W1)[:, 0, :]
+            dWm = dWm - t_[:, :, None] * dc[:, None, :]
+            self._pg_dst(st, [a.t for a in acts]).copy_((-(dc[:, None, :] @ Wm.transpose(1, 2)))[:, 0, :].unsqueeze(1))
+            self._pg_dst(st, [a.s for a in acts]).copy_((-(dWm * Wm).sum(dim=2) - sum_g).unsqueeze(1))
+            dWm = es[:, :, None] * dWm                                                  # d / d (P Lf Uf)
+        self._pg_dst(st, [b.linears[0].weight for b in blocks]).copy_(dW1)
+        self._pg_dst(st, [b.linears[0].bias for b in blocks]).copy_(db1)
         self._pg_dst(st, [b.linears[1].weight for b in blocks]).copy_(Gc[:, :, :W])
         self._pg_dst(st, [b.linears[1].bias for b in blocks]).copy_(Gc[:, :, W])
         if self._perm_dev is None or self._perm_dev.device != dev:
@@ -565,14 +666,11 @@ class B200RealNVP(TrainableDistribution):
         perm = self._perm_dev                     # kernel rows: shifts then scales; torch rows interleave them
         self._pg_dst(st, [b.linears[2].weight for b in blocks])[:, perm, :] = Gd[:, :, :W]
         self._pg_dst(st, [b.linears[2].bias for b in blocks])[:, perm] = Gd[:, :, W]
-        dWm = Gb.clone()
-        dWm[:, :, :d1] += dM1 @ W1
         A = P.transpose(1, 2) @ dWm
         dUf = Lf.transpose(1, 2) @ A
         self._pg_dst(st, [m.L for m in mixes]).copy_(torch.tril(A @ Uf.transpose(1, 2), diagonal=-1))
         self._pg_dst(st, [m.U for m in mixes]).copy_(torch.triu(dUf, diagonal=1))
-        self._pg_dst(st, [m.log_S for m in mixes]).copy_(
-            torch.diagonal(dUf, dim1=1, dim2=2) * sdiag + out[tail_off + 2 * d])
+        self._pg_dst(st, [m.log_S for m in mixes]).copy_(torch.diagonal(dUf, dim1=1, dim2=2) * sdiag + sum_g)
 
     def cuda_param_grad(self, tape: torch.Tensor, g: torch.Tensor):
         """Gradients of sum_i g_i log q(x_i) for every parameter, in `self.parameters()` order."""
@@ -590,7 +688,7 @@ class B200RealNVP(TrainableDistribution):
 
     # ---- the same maths in torch ops (GPU), differentiable w.r.t. parameters -----------------
     def _coupling_params(self, k, v1):
-        l1, l2, l3 = self._nf_model.flows[2 * k].linears
+        l1, l2, l3 = self._blocks()[k].linears
         h = torch.relu(l1(v1))
         h = torch.relu(l2(h))
         par = l3(h)
@@ -602,9 +700,11 @@ class B200RealNVP(TrainableDistribution):
         log_q = torch.zeros(len(x), dtype=x.dtype, device=x.device)
         z = x
         if self.n_flow_layers:
-            W, _, logs = self._mixing(x.dtype)
+            W, _, logs, c, _ = self._mixing(x.dtype)
         for k in range(self.n_flow_layers - 1, -1, -1):
             v = z @ W[k]
+            if c is not None:
+                v = v + c[k]
             v1, v2 = v[:, :d1], v[:, d1:]
             shift, scale = self._coupling_params(k, v1)
             z = torch.cat([v1, (v2 - shift) * torch.exp(-scale)], dim=1)
@@ -619,11 +719,13 @@ class B200RealNVP(TrainableDistribution):
         log_q = -0.5 * self.dim * math.log(2 * math.pi) - torch.sum(
             q0.log_scale + 0.5 * eps ** 2, dim=1)
         if self.n_flow_layers:
-            _, W_inv, logs = self._mixing(eps.dtype)
+            _, W_inv, logs, _, t = self._mixing(eps.dtype)
         for k in range(self.n_flow_layers):
             v1, v2 = z[:, :d1], z[:, d1:]
             shift, scale = self._coupling_params(k, v1)
             z = torch.cat([v1, v2 * torch.exp(scale) + shift], dim=1) @ W_inv[k]
+            if t is not None:
+                z = z + t[k]
             log_q = log_q - scale.sum(dim=1) + logs[k]
         return z, log_q
 

@@ -80,8 +80,12 @@ extern "C" {
  *     o_mix_inv K16=D16   N8=D8     in = [v1,y2] M[k][n] = Wmix^-1[k][n]
  *     (o_w2, o_w3 are shared with the inverse direction)
  *   vectors:
- *     o_b1[D8+W8] = [0 (D8) | b1 (W8)]   (o_b1 + D8 is the plain b1 of the sampling direction)
- *     o_b2[W8] = b2;   o_b3[P8] = b3p;   o_logs[4] : [0] = sum(log_S) of this layer's InvertibleAffine
+ *     o_b1[D8+W8] = [c (D8) | b1 + c[:d1] @ W1^T (W8)]   bias of the merged inverse-direction GEMM
+ *     o_b2[W8] = b2;   o_b3[P8] = b3p;   o_logs[4] : [0] = log|det| of this layer's linear part
+ *     o_b1s[W8] = b1 (sampling direction);   o_tmix[D8] = t (added after @ Wmix^-1 when sampling)
+ *   ActNorm (make_normflow_model.py:28-29: z*exp(s)+t after the InvertibleAffine) is folded into
+ *   the linear part by the host: Wmix := diag(exp(-s)) W, Wmix^-1 := W^-1 diag(exp(s)),
+ *   c = -t @ Wmix, logs = sum(log_S) - sum(s).  Without ActNorm c = t = 0 and Wmix = W.
  * ------------------------------------------------------------------------------------- */
 typedef struct fab_flow_desc {
     int32_t dim;          /* d                                   */
@@ -98,6 +102,7 @@ typedef struct fab_flow_desc {
     int64_t o_w3t, o_w2t, o_w1mt;
     int64_t o_w1, o_mix_inv;
     int64_t o_b1, o_b2, o_b3, o_logs;
+    int64_t o_b1s, o_tmix;
 } fab_flow_desc;
 
 /* Fills every field of *desc from (dim, width, n_layers); returns total_floats or <0. */
@@ -342,7 +347,8 @@ int fab_ais_chain_hmc_f32(const fab_flow_desc* flow, const float* d_blob, const 
  *   fab_flow_param_grad_f32: weight gradients as batch-contraction GEMMs over the tape, written as
  *     dense blocks per layer
  *         Ga [(d+1) x W]   rows 0..d-1: dM1 = d/d(Wmix[:, :d1] W1^T), row d: d/d b1
- *         Gb [d x d]       direct part of d/d Wmix   (full: Gb + [dM1 W1 | 0])
+ *         Gb [(d+1) x d]   rows 0..d-1: direct part of d/d Wmix (full: Gb + [dM1 W1 | 0]); row d: d/d c
+ *                          (the bias of v = z @ Wmix + c: the folded ActNorm shift)
  *         Gc [W x (W+1)]   d/d W2 ([out][in]) | d/d b2
  *         Gd [2 d2 x (W+1)] d/d W3 (rows: the d2 shifts, then the d2 scales) | d/d b3
  *     then [d/d loc (d) | d/d log_scale (d) | sum_i g_i (= d/d sum(log_S) of every layer)].

@@ -34,7 +34,8 @@ def layer_views(blob, d, k):
     return dict(mw1=g(d.o_mw1, D16, D8 + W8), w2=g(d.o_w2, W16, W8), w3=g(d.o_w3, W16, P8),
                 w3t=g(d.o_w3t, P16, W8), w2t=g(d.o_w2t, W16, W8), w1mt=g(d.o_w1mt, W16 + D16, D8),
                 w1=g(d.o_w1, D1K, W8), mix_inv=g(d.o_mix_inv, D16, D8),
-                b1=v(d.o_b1, D8 + W8), b2=v(d.o_b2, W8), b3=v(d.o_b3, P8), logs=blob[base + d.o_logs])
+                b1=v(d.o_b1, D8 + W8), b2=v(d.o_b2, W8), b3=v(d.o_b3, P8), logs=blob[base + d.o_logs],
+                b1s=v(d.o_b1s, W8), tmix=v(d.o_tmix, D8))
 
 
 def _pad(a, width):
@@ -98,13 +99,13 @@ def interp_sample(blob, d, eps):
     for k in range(d.n_layers):
         L = layer_views(blob, d, k)
         # the kernel feeds rows [0, D1K) of the z operand: rows >= d1 meet zero weight rows
-        h1 = np.maximum(_pad(z, max(D16, D1K))[:, :D1K] @ L["w1"] + L["b1"][D8:], 0)
+        h1 = np.maximum(_pad(z, max(D16, D1K))[:, :D1K] @ L["w1"] + L["b1s"], 0)
         h2 = np.maximum(_pad(h1, W16) @ L["w2"] + L["b2"], 0)
         par = _pad(h2, W16) @ L["w3"] + L["b3"]
         shift, scale = par[:, :d2], par[:, d2:2 * d2]
         y = np.zeros((len(eps), D16))
         y[:, :d1] = z[:, :d1]
         y[:, d1:dim] = z[:, d1:] * np.exp(scale) + shift
-        z = (y @ L["mix_inv"])[:, :dim]
+        z = (y @ L["mix_inv"] + L["tmix"])[:, :dim]
         lq += L["logs"] - scale.sum(1)
     return z, lq

@@ -8,19 +8,30 @@ from oracle.realnvp import OracleRealNVP, randomize_last_layers
 from oracle.targets import OracleManyWell, OracleGMM, to_double
 
 
-def make_flows(dim, n_layers, nodes_per_dim, seed=0, last_std=0.05, perturb_base=True, device="cuda"):
-    """Returns (oracle fp64, oracle fp32, product on `device`) sharing the same fp32 weights."""
+def make_flows(dim, n_layers, nodes_per_dim, seed=0, last_std=0.05, perturb_base=True, device="cuda",
+               act_norm=False):
+    """Returns (oracle fp64, oracle fp32, product on `device`) sharing the same fp32 weights.  With
+    `act_norm` the ActNorm layers are initialised from data by the oracle's constructor (500 samples)
+    and then moved off their init so that shifts and scales are not near the identity."""
     torch.manual_seed(seed)
-    fo = OracleRealNVP(dim, n_layers, nodes_per_dim)
+    fo = OracleRealNVP(dim, n_layers, nodes_per_dim, act_norm=act_norm)
     if n_layers:
         randomize_last_layers(fo, last_std, seed=seed + 1)
+    if act_norm:
+        g = torch.Generator().manual_seed(seed + 3)
+        with torch.no_grad():
+            for name, p in fo.named_parameters():
+                if name.endswith(".s"):
+                    p.add_(torch.randn(p.shape, generator=g) * 0.05)
+                elif name.endswith(".t"):
+                    p.add_(torch.randn(p.shape, generator=g) * 0.15)
     if perturb_base:
         g = torch.Generator().manual_seed(seed + 2)
         with torch.no_grad():
             fo._nf_model.q0.loc.add_(torch.randn(1, dim, generator=g) * 0.2)
             fo._nf_model.q0.log_scale.add_(torch.randn(1, dim, generator=g) * 0.1)
     fo64 = copy.deepcopy(fo).double()
-    fp = fb.B200RealNVP(dim, n_layers, nodes_per_dim)
+    fp = fb.B200RealNVP(dim, n_layers, nodes_per_dim, act_norm=act_norm)
     fp.load_state_dict(fo.state_dict())
     if device is not None:
         fp = fp.to(device)

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound(L):
 
 def test_struct_sizes_match_header(L):
     # natural C alignment of the header structs
-    assert C.sizeof(_lib.FlowDesc) == 8 * 4 + 17 * 8      # 7 int32 + pad, 17 int64
+    assert C.sizeof(_lib.FlowDesc) == 8 * 4 + 19 * 8      # 7 int32 + pad, 19 int64
     assert C.sizeof(_lib.Gamma) == 16
     assert C.sizeof(_lib.PointPtrs) == 40
     assert C.sizeof(_lib.TargetDesc) == 8 * 4 + 3 * 8
@@ -50,9 +50,9 @@ def test_flow_desc_init(L):
     assert (d.dim, d.d1, d.d2, d.width_pad, d.width_kpad, d.n_layers) == (32, 16, 16, 320, 320, 10)
     # fragment-ordered operands (K16 x N8): o_mw1 (32x352) o_w2 (320x320) o_w3 (320x32)
     # o_w3t (32x320) o_w2t (320x320) o_w1mt (352x32) o_w1 (16x320) o_mix_inv (32x32);
-    # vectors o_b1 (352) o_b2 (320) o_b3 (32) o_logs (4)
+    # vectors o_b1 (352) o_b2 (320) o_b3 (32) o_logs (4) o_b1s (320) o_tmix (32)
     per_layer = (32 * 352 + 320 * 320 + 320 * 32 + 32 * 320 + 320 * 320 + 352 * 32 + 16 * 320 + 32 * 32
-                 + 352 + 320 + 32 + 4)
+                 + 352 + 320 + 32 + 4 + 320 + 32)
     assert d.layer_stride == per_layer
     assert d.total_floats == 64 + 10 * per_layer + 512
     assert L.fab_flow_desc_init(d, 5, 15, 2) > 0

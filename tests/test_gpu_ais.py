@@ -15,8 +15,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_pair(dim, K, npd, tk, M, B, op_kind, spacing="linear", p_target=False, alpha=2.0,
-              last_std=0.05, **opkw):
-    fo64, fo, fp = make_flows(dim, K, npd, last_std=last_std)
+              last_std=0.05, act_norm=False, **opkw):
+    fo64, fo, fp = make_flows(dim, K, npd, last_std=last_std, act_norm=act_norm)
     if tk == "mw":
         to, tp = make_manywell(dim)
         to32 = to
@@ -68,6 +68,9 @@ AIS_CASES = [
     dict(dim=128, K=10, npd=10, tk="mw", M=2, B=24, op_kind="hmc", epsilon=0.02, L=2, last_std=0.003),
     # BASELINE config 5: 60-dof ALDP surrogate energy, 20 distributions, HMC L=4 (fab_buff.yaml:43)
     dict(dim=60, K=4, npd=5, tk="aldp", M=20, B=64, op_kind="hmc", epsilon=0.05, L=4),
+    # ActNorm after every InvertibleAffine (make_normflow_model.py:28-29), folded into the packed weights
+    dict(dim=32, K=5, npd=10, tk="mw", M=4, B=160, op_kind="hmc", epsilon=0.05, L=3, act_norm=True),
+    dict(dim=2, K=3, npd=20, tk="gmm", M=5, B=256, op_kind="metropolis", n_updates=2, act_norm=True),
 ]
 
 

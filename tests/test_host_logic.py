@@ -10,9 +10,10 @@ from helpers import make_flows
 from oracle.sampler import OracleHMC, OracleMetropolis, Point as OPoint, beta_schedule, gamma, grad_gamma
 
 
-@pytest.mark.parametrize("dim,K,npd", [(32, 3, 10), (2, 4, 40), (5, 2, 3), (6, 2, 7), (9, 1, 5)])
-def test_packed_blob_matches_oracle(dim, K, npd):
-    fo64, fo, fp = make_flows(dim, K, npd, device=None)
+@pytest.mark.parametrize("dim,K,npd,act_norm", [(32, 3, 10, False), (2, 4, 40, False), (5, 2, 3, False), (6, 2, 7, False),
+                                                 (9, 1, 5, False), (6, 3, 7, True), (5, 2, 3, True)])
+def test_packed_blob_matches_oracle(dim, K, npd, act_norm):
+    fo64, fo, fp = make_flows(dim, K, npd, device=None, act_norm=act_norm)
     x = torch.randn(11, dim, dtype=torch.float64).requires_grad_(True)
     lq = fo64.log_prob(x)
     g = torch.autograd.grad(lq.sum(), x)[0]
@@ -40,8 +41,36 @@ def test_same_seed_same_weights_and_state_dict_keys():
     assert b.event_shape == (6,)
 
 
-def test_torch_restatement_in_product_matches_oracle():
-    fo64, fo, fp = make_flows(6, 3, 4, device=None)
+def test_act_norm_same_seed_same_init_and_state_dict_keys():
+    """make_normflow_model.py:28-29,94-95: ActNorm after every InvertibleAffine, initialised from the
+    statistics of 500 samples at construction.  Same seed -> the same s, t as the oracle restatement
+    (same RNG consumption, same arithmetic), normflows-style keys, and the init leaves every layer's
+    output standardised for that batch."""
+    from oracle.realnvp import OracleRealNVP
+    torch.manual_seed(5)
+    a = OracleRealNVP(6, 3, 4, act_norm=True)
+    torch.manual_seed(5)
+    b = fb.B200RealNVP(6, 3, 4, act_norm=True)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.allclose(sa[k], sb[k], rtol=0, atol=1e-6), k
+    assert "_nf_model.flows.2.s" in sb and "_nf_model.flows.8.t" in sb
+    assert float(sb["_nf_model.flows.5.data_dep_init_done"]) == 1.0
+    assert sb["_nf_model.flows.2.s"].abs().max() > 1e-3          # the init did something
+    assert not fb.B200RealNVP(6, 0, 4, act_norm=True).act_norm    # no layers: nothing to normalise
+    # a second construction consumes the RNG the same way (randn(500, d) once)
+    torch.manual_seed(5)
+    fb.B200RealNVP(6, 3, 4, act_norm=True)
+    r1 = torch.rand(1)
+    torch.manual_seed(5)
+    OracleRealNVP(6, 3, 4, act_norm=True)
+    assert torch.equal(r1, torch.rand(1))
+
+
+@pytest.mark.parametrize("act_norm", [False, True])
+def test_torch_restatement_in_product_matches_oracle(act_norm):
+    fo64, fo, fp = make_flows(6, 3, 4, device=None, act_norm=act_norm)
     x = torch.randn(20, 6)
     assert torch.allclose(fp.torch_log_prob(x), fo.log_prob(x), atol=2e-5)
     eps = torch.randn(20, 6)
@@ -102,8 +131,6 @@ def test_no_cpu_fallback():
     with pytest.raises(TypeError):
         fb.HamiltonianMonteCarlo(2, 4, fp.log_prob, torch.distributions.Normal(0., 1.).log_prob,
                                  alpha=2.0)
-    with pytest.raises(NotImplementedError):
-        fb.B200RealNVP(4, 1, 3, act_norm=True)
 
 
 def test_point_mask_semantics():
