@@ -159,8 +159,7 @@ class B200RealNVP(TrainableDistribution):
     28-29) and, like the reference factory (:94-95), draws 500 samples once to set s, t from the
     batch statistics.  The kernels never see the layer: the host folds it into the block's linear
     part (Wmix := diag(exp(-s)) W, bias c = -t @ Wmix, log|det| = sum(log_S) - sum(s); include/
-    fab_b200.h) when it packs the weights.  With ActNorm the warp-level engine evaluates the flow
-    (the row-tile engine's issue program has no bias row for the v columns)."""
+    fab_b200.h) when it packs the weights (both engines)."""
 
     def __init__(self, dim: int, n_flow_layers: int = 5, layer_nodes_per_dim: int = 10,
                  act_norm: bool = False):
@@ -411,7 +410,7 @@ class B200RealNVP(TrainableDistribution):
 
     # ---- row-tile engine (tcgen05): weight images and engine choice ------------------------------
     def rowtile_supported(self) -> bool:
-        return not self.act_norm and bool(_lib.lib().fab_umma_supported(self.desc()))
+        return bool(_lib.lib().fab_umma_supported(self.desc()))
 
     def use_rowtile(self, n: int) -> bool:
         mode = _lib.engine_choice()
@@ -420,7 +419,7 @@ class B200RealNVP(TrainableDistribution):
         if not self.rowtile_supported():
             if mode == "rowtile":
                 raise RuntimeError("FAB_ENGINE=rowtile: this flow shape is not covered by the row-tile "
-                                   "engine (needs dim 32, width 64..320 in steps of 64, <= 10 layers, no ActNorm)")
+                                   "engine (needs dim 32, width 64..320 in steps of 64, <= 10 layers)")
             return False
         return mode == "rowtile" or n >= _lib.rowtile_min_n()
 
@@ -466,10 +465,13 @@ class B200RealNVP(TrainableDistribution):
         dev = W1.device
         perm = torch.cat([torch.arange(0, 2 * d.d2, 2, device=dev), torch.arange(1, 2 * d.d2, 2, device=dev)])
         W3, b3 = W3[:, perm, :], b3[:, perm]
-        Wm, _, logs, _, _ = self._mixing_pack(need_inverse=False)
+        Wm, _, logs, cmix, _ = self._mixing_pack(need_inverse=False)
         t = lambda M: M.transpose(1, 2)
         mw1 = torch.cat([Wm, (Wm[:, :, :d1].double() @ t(W1).double()).float()], dim=2)   # [K, d, d+W]
-        b1e = torch.cat([b1.new_zeros(K, dd), b1], dim=1)
+        if cmix is None:
+            b1e = torch.cat([b1.new_zeros(K, dd), b1], dim=1)
+        else:                                     # folded ActNorm: v = z @ Wmix + c, h1pre bias b1 + c[:d1] @ W1^T
+            b1e = torch.cat([cmix, (b1.double() + (cmix[:, None, :d1].double() @ t(W1).double())[:, 0, :]).float()], dim=1)
         w1mt = (W1.double() @ t(Wm[:, :, :d1]).double()).float()                         # [K, W, d]
         mats = [(mw1, b1e), (t(W2), b2), (t(W3), b3), (W3, None), (W2, None), (w1mt, None), (t(Wm), None)]
         layer = W1.new_zeros(K, per_layer)

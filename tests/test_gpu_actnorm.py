@@ -14,11 +14,12 @@ pytestmark = pytest.mark.gpu
 CASES = [(32, 10, 10), (2, 4, 40), (5, 3, 3), (60, 4, 5)]
 
 
-@pytest.mark.parametrize("dim,K,npd", CASES)
+@pytest.mark.parametrize("dim,K,npd,engine", [c + ("warp",) for c in CASES] + [(32, 10, 10, "rowtile"), (32, 3, 4, "rowtile")])
 @pytest.mark.parametrize("n", [1, 300, 2048])
-def test_log_prob_grad_and_sample_with_act_norm(dim, K, npd, n):
+def test_log_prob_grad_and_sample_with_act_norm(dim, K, npd, engine, n, monkeypatch):
+    monkeypatch.setenv("FAB_ENGINE", engine)
     fo64, fo, fp = make_flows(dim, K, npd, act_norm=True, last_std=0.02 if K >= 10 else 0.05)
-    assert fp.act_norm and not fp.rowtile_supported()
+    assert fp.act_norm and fp.use_rowtile(n) == (engine == "rowtile")
     g = torch.Generator().manual_seed(5)
     x = torch.randn(n, dim, generator=g) * 1.5
     x64 = x.double().requires_grad_(True)

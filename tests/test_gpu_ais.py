@@ -71,11 +71,14 @@ AIS_CASES = [
     # ActNorm after every InvertibleAffine (make_normflow_model.py:28-29), folded into the packed weights
     dict(dim=32, K=5, npd=10, tk="mw", M=4, B=160, op_kind="hmc", epsilon=0.05, L=3, act_norm=True),
     dict(dim=2, K=3, npd=20, tk="gmm", M=5, B=256, op_kind="metropolis", n_updates=2, act_norm=True),
+    dict(dim=32, K=5, npd=10, tk="mw", M=4, B=160, op_kind="hmc", epsilon=0.05, L=3, act_norm=True, engine="rowtile"),
 ]
 
 
 @pytest.mark.parametrize("case", AIS_CASES)
-def test_chain_parity(case):
+def test_chain_parity(case, monkeypatch):
+    case = dict(case)
+    monkeypatch.setenv("FAB_ENGINE", case.pop("engine", "auto"))
     (pt_o, lw_o, ais_o, op_o), (pt_p, lw_p, ais_p, op_p) = _run_pair(**case)
     assert lw_p.shape == lw_o.shape and pt_p.x.shape == pt_o.x.shape
     B = lw_o.shape[0]
