@@ -155,3 +155,6 @@ def test_state_dict_keys_follow_normflows_fixture():
     import fab_torch_b200 as fb
     flow = fb.B200RealNVP(4, fx["n_flow_layers"], 3)
     assert sorted(flow.state_dict().keys()) == fx["keys"]
+    flow = fb.B200RealNVP(4, fx["n_flow_layers"], 3, act_norm=True)
+    assert sorted(flow.state_dict().keys()) == fx["keys_act_norm"]
+    assert "_nf_model.flows.2.s" in fx["keys_act_norm"] and "_nf_model.flows.2.data_dep_init_done" in fx["keys_act_norm"]
