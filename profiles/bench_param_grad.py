@@ -30,7 +30,7 @@ if __name__ == "__main__":
         flow = fb.B200RealNVP(dim, K, npd).cuda()
         with torch.no_grad():
             for k in range(K):
-                lin = flow._nf_model.flows[2 * k].linears[2]
+                lin = flow._blocks()[k].linears[2]
                 lin.weight.normal_(0, 0.02); lin.bias.normal_(0, 0.02)
         x = torch.randn(n, dim, device="cuda")
         w = torch.softmax(torch.randn(n, device="cuda"), 0)
