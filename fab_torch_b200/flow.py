@@ -268,11 +268,23 @@ class B200RealNVP(TrainableDistribution):
             st["warm"] = True
             return
         if st["graph"] is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
-            st["graph"] = g
+            # (thread-local capture mode: `backward` runs this on the autograd thread while other
+            # threads of the process -- data loaders, loggers -- may be calling into CUDA)
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    fn()
+                st["graph"] = g
+            except Exception as e:               # noqa: BLE001 -- a failed capture only costs the replay speed-up
+                import warnings
+                warnings.warn(f"fab_torch_b200: CUDA-graph capture of '{which}' failed ({type(e).__name__}: {e}); "
+                              "running it eagerly from now on")
+                st["graph"] = False
+                torch.cuda.synchronize()
+        if st["graph"] is False:
+            fn()
+            return
         st["graph"].replay()
 
     def blob(self) -> torch.Tensor:

@@ -102,7 +102,7 @@ def test_param_grad_follows_parameter_updates_through_the_captured_chain_rule():
                 step = 0.05 * torch.randn(p2.shape, generator=g, dtype=torch.float64)
                 p2.add_(step)
                 p1.add_(step.float().cuda())
-    assert f"pg{len(x)}" in fp._pack_graphs and fp._pack_graphs[f"pg{len(x)}"]["graph"] is not None
+    assert isinstance(fp._pack_graphs.get(f"pg{len(x)}", {}).get("graph"), torch.cuda.CUDAGraph)
     for held, copies in kept:
         for a, b in zip(held, copies):
             assert torch.equal(a, b)
