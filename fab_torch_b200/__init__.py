@@ -12,6 +12,6 @@ from fab_torch_b200.numerical import effective_sample_size
 from fab_torch_b200.resample import (systematic_resample, systematic_ancestors,
                                       global_systematic_resample, resample_if_ess_below)
 
-from fab_torch_b200.replay_buffer import PrioritisedReplayBuffer, ReplayData
+from fab_torch_b200.replay_buffer import PrioritisedReplayBuffer, ReplayData, ReplayBuffer, AISData
 
 __version__ = "0.1"

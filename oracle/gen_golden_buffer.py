@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from oracle.buffer import OracleBuffer, gumbel_like, topk_set     # noqa: E402
+from oracle.buffer import (OracleBuffer, gumbel_like, topk_set, OracleReplayBuffer,   # noqa: E402
+                           exponential_like, race_topk)
 from oracle.ref_loader import load_reference                       # noqa: E402
 
 
@@ -86,5 +87,60 @@ def main():
           f"({os.path.getsize(path) / 1e3:.0f} kB)")
 
 
+def main_uniform():
+    """fab/utils/replay_buffer.py (the buffer of fab/train_with_buffer.py): fill by `initial_sampler`, adds that
+    wrap the ring, `sample_n_batches` at temperature 1 (the default), 0 (uniform) -- the exponential variates of
+    torch.multinomial are recorded by re-seeding -- more adds, another sample.  Writes tests/golden/replay_buffer.pt."""
+    load_reference()
+    from fab.utils.replay_buffer import ReplayBuffer as RefBuffer
+    dim, max_length, min_len, B = 5, 400, 150, 64
+    out = dict(config=dict(dim=dim, max_length=max_length, min_sample_length=min_len, batch=B), runs=[])
+    for temperature in (1.0, 0.0):
+        g = torch.Generator().manual_seed(11)
+        batches = [(torch.randn(B, dim, generator=g), torch.randn(B, generator=g) * 2) for _ in range(14)]
+        it = iter(batches)
+        ref = RefBuffer(dim, max_length, min_len, lambda: next(it), device="cpu", temperature=temperature)
+        orc = OracleReplayBuffer(dim, max_length, min_len, temperature=temperature)
+        it2 = iter(batches)
+        orc.fill(lambda: next(it2))
+        n_init = sum(1 for _ in range(len(batches))) - sum(1 for _ in it2)
+
+        def same_state():
+            return (torch.equal(ref.buffer.x, orc.x) and torch.equal(ref.buffer.log_w, orc.log_w)
+                    and torch.equal(ref.buffer.add_count, orc.add_count) and ref.current_index == orc.current_index
+                    and ref.current_add_count == orc.current_add_count and ref.is_full == orc.is_full
+                    and ref.can_sample == orc.can_sample)
+
+        def snap():
+            return dict(x=orc.x.clone(), log_w=orc.log_w.clone(), add_count=orc.add_count.clone(),
+                        current_index=orc.current_index, current_add_count=orc.current_add_count,
+                        is_full=orc.is_full, can_sample=orc.can_sample)
+
+        assert same_state(), "init fill differs"
+        steps = [dict(op="init", n_batches=n_init, state=snap())]
+        k_next = n_init
+        for rnd in range(3):
+            for _ in range(3):                                   # 3 x 64 rows per round: wraps in round 2
+                b = batches[k_next]; k_next += 1
+                ref.add(*b); orc.add(*b)
+                assert same_state(), "add differs"
+                steps.append(dict(op="add", state=snap()))
+            k = 32 * 3
+            torch.manual_seed(200 + rnd)
+            q = exponential_like(orc.probs())                    # what torch.multinomial will draw
+            torch.manual_seed(200 + rnd)
+            data = ref.sample_n_batches(32, 3)
+            x_r, lw_r = torch.cat([d[0] for d in data]), torch.cat([d[1] for d in data])
+            x_o, lw_o, idx_o = orc.sample(k, q=q)
+            assert torch.equal(x_r, x_o) and torch.equal(lw_r, lw_o), "sampled rows differ"
+            steps.append(dict(op="sample", k=k, q=q, indices=idx_o.clone(), x=x_r.clone(), log_w=lw_r.clone()))
+        out["runs"].append(dict(temperature=temperature, batches=batches, steps=steps))
+    path = os.path.join(ROOT, "tests", "golden", "replay_buffer.pt")
+    torch.save(out, path)
+    print(f"oracle replay buffer == reference ReplayBuffer on every step (temperature 1 and 0); wrote {path} "
+          f"({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     main()
+    main_uniform()

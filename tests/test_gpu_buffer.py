@@ -110,3 +110,59 @@ def test_config5_chain_feeds_the_buffer():
     buf.adjust(adj, lq_new, idx)
     assert torch.allclose(buf.buffer.log_w[idx], before + adj) and torch.equal(buf.buffer.log_q_old[idx], lq_new)
     assert torch.isfinite(buf.buffer.log_w[:512]).all()
+
+
+# ---- fab/utils/replay_buffer.py (un-prioritised buffer) ------------------------------------------
+def test_cuda_replay_buffer_matches_reference_fixture():
+    """Device ReplayBuffer vs the fixture written by the unmodified reference class: ring state bit-exact,
+    sampled rows identical and in the reference's order when the exponential variates are the recorded ones."""
+    from test_oracle_buffer import replay_uniform, _init_add
+
+    def make(c, T):
+        return fb.ReplayBuffer(c["dim"], c["max_length"], c["min_sample_length"], _never, device="cuda",
+                               temperature=T, fill_buffer_during_init=False)
+
+    def sample(b, k, q):
+        max_index = b.max_length if b.is_full else b.current_index
+        rank = b.current_add_count - b.buffer.add_count[:max_index]
+        idx = b._race(torch.pow(1 / rank, b.temperature), q.cuda(), k)
+        return b.buffer.x[idx], b.buffer.log_w[idx], idx
+    replay_uniform(make, _init_add, sample,
+                   lambda b: dict(x=b.buffer.x, log_w=b.buffer.log_w, add_count=b.buffer.add_count,
+                                  current_index=b.current_index, current_add_count=b.current_add_count,
+                                  is_full=b.is_full, can_sample=b.can_sample))
+
+
+def test_replay_buffer_interface_and_seeded_sampling():
+    """Constructor fill loop, sample_n_batches, and: the same seed gives the rows the reference algorithm
+    (oracle restatement on the same RNG call) samples; newer batches are preferred at temperature 1."""
+    from oracle.buffer import OracleReplayBuffer
+    dim, N, B = 6, 3000, 500
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(B, dim, generator=g), torch.randn(B, generator=g)) for _ in range(9)]
+    it, it2 = iter(batches), iter(batches)
+    buf = fb.ReplayBuffer(dim, N, 900, lambda: next(it), device="cuda")
+    orc = OracleReplayBuffer(dim, N, 900)
+    orc.fill(lambda: next(it2))
+    assert buf.can_sample and buf.current_index == 1000 and buf.current_add_count == 1
+    for b in it:
+        buf.add(*b)
+    for b in it2:
+        orc.add(*b)
+    assert buf.is_full and buf.current_index == orc.current_index == 1500
+    assert torch.equal(buf.buffer.add_count.cpu(), orc.add_count)
+    torch.manual_seed(4)
+    data = buf.sample_n_batches(100, 4)
+    torch.manual_seed(4)
+    x_o, lw_o, idx_o = orc.sample(400)
+    assert len(data) == 4 and data[0][0].shape == (100, dim)
+    assert torch.equal(torch.cat([d[0] for d in data]).cpu(), x_o) and torch.equal(torch.cat([d[1] for d in data]).cpu(), lw_o)
+    assert idx_o.unique().numel() == 400
+    # rank weighting: rows of the latest add (rank 1) are drawn far more often than the oldest (rank 6)
+    newest = ((idx_o >= 1000) & (idx_o < 1500)).sum().item()
+    oldest = ((idx_o >= 1500) & (idx_o < 2000)).sum().item()
+    assert newest > 2 * oldest
+    with pytest.raises(Exception):
+        fb.ReplayBuffer(dim, N, 900, _never, device="cuda", fill_buffer_during_init=False).sample(10)
+    with pytest.raises(RuntimeError):
+        fb.ReplayBuffer(dim, N, 10, _never, device="cpu", fill_buffer_during_init=False)
