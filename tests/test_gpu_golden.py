@@ -23,7 +23,7 @@ from oracle.targets import OracleGMM, OracleManyWell
 
 pytestmark = pytest.mark.gpu
 FIXTURES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt"))
-                  if not os.path.basename(p).startswith(("prioritised_buffer", "eval_")))   # test_*_buffer.py
+                  if not os.path.basename(p).startswith(("prioritised_buffer", "replay_buffer", "eval_")))   # test_*_buffer.py
 
 
 def build_product(fx):

@@ -16,7 +16,7 @@ from oracle.targets import OracleGMM, OracleManyWell, to_double
 from golden_util import GOLDEN_DIR, load_fixture, rebuild_flow, rebuild_target
 
 FIXTURES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt"))
-                  if not os.path.basename(p).startswith(("prioritised_buffer", "eval_")))   # test_oracle_buffer.py
+                  if not os.path.basename(p).startswith(("prioritised_buffer", "replay_buffer", "eval_")))   # test_oracle_buffer.py
 
 
 def test_pin_report_is_green():
