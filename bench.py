@@ -475,12 +475,12 @@ def run_gpu_arm(args):
             except Exception as e:           # noqa: BLE001 -- an extra leg must never cost the headline line
                 line["full_chip_batch"] = dict(error=f"{type(e).__name__}: {e}")
         if world == 1 and not args.no_cpu_baseline:
-            ts, cinfo, kind = time_cpu(cfg, B_local, steps=2, warmup=1)
+            ts, cinfo, kind = time_cpu(cfg, B_local, steps=7, warmup=1)      # ~10 s of CPU work
             cv = B_local * len(ts) / float(np.sum(ts))
             ts64, _, _ = time_cpu(cfg, B_local, steps=1, warmup=0, dtype=torch.float64)
             line["cpu_baseline"] = dict(
                 value=cv, unit=UNIT, cores=torch.get_num_threads(), kind=kind,
-                sample=f"2 timed + 1 warm-up full sample_and_log_weights({B_local}) calls through the "
+                sample=f"{len(ts)} timed + 1 warm-up full sample_and_log_weights({B_local}) calls through the "
                        f"{'unmodified reference classes (baseline/_ref)' if kind == 'reference' else 'oracle port'}, "
                        f"fp32, {float(np.sum(ts)):.1f} s of CPU work",
                 fp64_value=B_local / float(ts64[0]),
