@@ -31,7 +31,7 @@ def build(device, group):
     target = fb.ManyWellEnergy(32)
     M = 6
     op = fb.HamiltonianMonteCarlo(M, 32, flow.log_prob, target.log_prob, alpha=2.0, p_target=False,
-                                  epsilon=0.3, n_outer=2, L=3).to(device)
+                                  epsilon=0.05, n_outer=2, L=3).to(device)
     ais = fb.AnnealedImportanceSampler(flow, target.log_prob, op, p_target=False, alpha=2.0,
                                        n_intermediate_distributions=M, process_group=group)
     return flow, op, ais, M
